@@ -1,0 +1,101 @@
+"""ctypes binding of libesrp.so (C ABI declared in include/esrp.h).
+
+The product path has no CPU or PyTorch fallback: if the shared library is missing or a call
+fails, a RuntimeError is raised.  Build it with ``python -c "import __graft_entry__ as g; g.build()"``
+or ``make -C esrganplus_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+ESRP_MAX_CHUNKS = 8
+VARIANT_ALIGNED = 1
+VARIANT_MT1 = 2
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libesrp.so")
+
+
+class Conv3x3Desc(C.Structure):
+    """Mirror of ``esrp_conv3x3_t`` (include/esrp.h) — field order and types must match."""
+
+    _fields_ = [
+        ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+        ("src", C.c_void_p * 2),
+        ("src_ctotal", C.c_int32 * 2),
+        ("kc", C.c_int32),
+        ("num_chunks", C.c_int32),
+        ("chunk_src", C.c_int32 * ESRP_MAX_CHUNKS),
+        ("chunk_c0", C.c_int32 * ESRP_MAX_CHUNKS),
+        ("aux_chunks", C.c_int32),
+        ("bn", C.c_int32),
+        ("cout", C.c_int32),
+        ("w_packed", C.c_void_p),
+        ("w_aux", C.c_void_p),
+        ("bias", C.c_void_p),
+        ("act", C.c_int32),
+        ("s0", C.c_float),
+        ("r1", C.c_void_p),
+        ("r1_is_f32", C.c_int32), ("r1_ctotal", C.c_int32), ("r1_c0", C.c_int32),
+        ("s1", C.c_float),
+        ("r2", C.c_void_p),
+        ("r2_is_f32", C.c_int32), ("r2_ctotal", C.c_int32), ("r2_c0", C.c_int32),
+        ("s2", C.c_float),
+        ("noise", C.c_int32),
+        ("sigma", C.c_float),
+        ("seed", C.c_uint64), ("offset", C.c_uint64),
+        ("out_bf16", C.c_void_p),
+        ("ob_ctotal", C.c_int32), ("ob_c0", C.c_int32),
+        ("out_f32", C.c_void_p),
+        ("of_ctotal", C.c_int32), ("of_c0", C.c_int32),
+        ("out_nchw", C.c_void_p),
+        ("variant", C.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); the single source of truth for the symbols tests check.
+SYMBOLS = {
+    "esrp_last_error": (C.c_char_p, []),
+    "esrp_version": (C.c_int, []),
+    "esrp_sm_count": (C.c_int, []),
+    "esrp_conv3x3_nhwc": (C.c_int, [C.POINTER(Conv3x3Desc), C.c_void_p]),
+    "esrp_packed_conv3x3_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "esrp_packed_conv1x1_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "esrp_pack_conv3x3_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_int32, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]),
+    "esrp_pack_conv1x1_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_int32, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]),
+    "esrp_nchw_f32_to_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                             C.c_int32, C.c_int32, C.c_void_p]),
+    "esrp_nhwc_bf16_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                             C.c_int32, C.c_int32, C.c_void_p]),
+    "esrp_upsample2x_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_int32, C.c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libesrp.so once; raise (never fall back) when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: the CUDA extension is not built. "
+                "Run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
+                "There is no CPU/PyTorch fallback for the hot path.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().esrp_last_error()
+        raise RuntimeError(f"libesrp {what} failed: {msg.decode() if msg else rc}")

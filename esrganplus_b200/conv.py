@@ -1,0 +1,163 @@
+"""Host-side helpers over the C ABI for one fused conv launch (PyTorch is plumbing only: it owns
+device memory and the stream; all arithmetic happens in libesrp.so)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import Conv3x3Desc
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _i32_array(vals: Sequence[int]):
+    arr = (C.c_int32 * len(vals))(*vals)
+    return arr
+
+
+def pack_conv3x3_weights(w_oihw: torch.Tensor, kc: int, bn: int, chunk_lc0: Sequence[int]) -> torch.Tensor:
+    """OIHW fp32 (device) -> pre-swizzled bf16 UMMA B tiles [chunk][tap][bn][kc] (opaque bytes)."""
+    lib = _lib.load()
+    assert w_oihw.is_cuda and w_oihw.dtype == torch.float32 and w_oihw.dim() == 4
+    w = w_oihw.contiguous()
+    cout, cin, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    nbytes = lib.esrp_packed_conv3x3_bytes(len(chunk_lc0), kc, bn)
+    out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    _lib.check(lib.esrp_pack_conv3x3_weights(w.data_ptr(), cout, cin, kc, bn, len(chunk_lc0),
+                                             _i32_array(chunk_lc0), out.data_ptr(), _stream_ptr()),
+               "esrp_pack_conv3x3_weights")
+    return out
+
+
+def pack_conv1x1_weights(w: torch.Tensor, kc: int, bn: int, chunk_lc0: Sequence[int]) -> torch.Tensor:
+    lib = _lib.load()
+    assert w.is_cuda and w.dtype == torch.float32
+    w2 = w.reshape(w.shape[0], w.shape[1]).contiguous()
+    cout, cin = w2.shape
+    nbytes = lib.esrp_packed_conv1x1_bytes(len(chunk_lc0), kc, bn)
+    out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    _lib.check(lib.esrp_pack_conv1x1_weights(w2.data_ptr(), cout, cin, kc, bn, len(chunk_lc0),
+                                             _i32_array(chunk_lc0), out.data_ptr(), _stream_ptr()),
+               "esrp_pack_conv1x1_weights")
+    return out
+
+
+@dataclass
+class ConvCall:
+    """Python-side description of one esrp_conv3x3_nhwc launch."""
+
+    n: int
+    h: int
+    w: int
+    srcs: List[torch.Tensor]                 # 1 or 2 NHWC bf16 tensors
+    kc: int
+    chunks: List[tuple]                      # [(src_index, c0), ...]
+    bn: int
+    cout: int
+    w_packed: torch.Tensor
+    bias: Optional[torch.Tensor] = None      # fp32 [bn]
+    w_aux: Optional[torch.Tensor] = None
+    aux_chunks: int = 0
+    act: int = 0
+    s0: float = 1.0
+    r1: Optional[torch.Tensor] = None
+    r1_c0: int = 0
+    s1: float = 1.0
+    r2: Optional[torch.Tensor] = None
+    r2_c0: int = 0
+    s2: float = 1.0
+    noise: int = 0
+    sigma: float = 0.1
+    seed: int = 0
+    offset: int = 0
+    out_bf16: Optional[torch.Tensor] = None
+    ob_c0: int = 0
+    out_f32: Optional[torch.Tensor] = None
+    of_c0: int = 0
+    out_nchw: Optional[torch.Tensor] = None
+    variant: int = 0
+    _keep: list = field(default_factory=list, repr=False)
+
+    def desc(self) -> Conv3x3Desc:
+        d = Conv3x3Desc()
+        d.n, d.h, d.w = self.n, self.h, self.w
+        for i, s in enumerate(self.srcs):
+            assert s.is_cuda and s.dtype == torch.bfloat16 and s.is_contiguous()
+            assert s.shape[:3] == (self.n, self.h, self.w), (s.shape, (self.n, self.h, self.w))
+            d.src[i] = s.data_ptr()
+            d.src_ctotal[i] = s.shape[3]
+        d.kc = self.kc
+        d.num_chunks = len(self.chunks)
+        for i, (si, c0) in enumerate(self.chunks):
+            d.chunk_src[i] = si
+            d.chunk_c0[i] = c0
+        d.aux_chunks = self.aux_chunks
+        d.bn, d.cout = self.bn, self.cout
+        d.w_packed = self.w_packed.data_ptr()
+        d.w_aux = self.w_aux.data_ptr() if self.w_aux is not None else None
+        d.bias = self.bias.data_ptr() if self.bias is not None else None
+        d.act, d.s0 = self.act, self.s0
+        for name in ("r1", "r2"):
+            t = getattr(self, name)
+            if t is not None:
+                assert t.is_cuda and t.is_contiguous() and t.dtype in (torch.bfloat16, torch.float32)
+                setattr(d, name, t.data_ptr())
+                setattr(d, name + "_is_f32", int(t.dtype == torch.float32))
+                setattr(d, name + "_ctotal", t.shape[3])
+                setattr(d, name + "_c0", getattr(self, name + "_c0"))
+        d.s1, d.s2 = self.s1, self.s2
+        d.noise, d.sigma, d.seed, d.offset = self.noise, self.sigma, self.seed, self.offset
+        if self.out_bf16 is not None:
+            assert self.out_bf16.dtype == torch.bfloat16 and self.out_bf16.is_contiguous()
+            d.out_bf16, d.ob_ctotal, d.ob_c0 = self.out_bf16.data_ptr(), self.out_bf16.shape[3], self.ob_c0
+        if self.out_f32 is not None:
+            assert self.out_f32.dtype == torch.float32 and self.out_f32.is_contiguous()
+            d.out_f32, d.of_ctotal, d.of_c0 = self.out_f32.data_ptr(), self.out_f32.shape[3], self.of_c0
+        if self.out_nchw is not None:
+            assert self.out_nchw.dtype == torch.float32 and self.out_nchw.is_contiguous()
+            d.out_nchw = self.out_nchw.data_ptr()
+        d.variant = self.variant
+        return d
+
+    def launch(self) -> None:
+        lib = _lib.load()
+        d = self.desc()
+        _lib.check(lib.esrp_conv3x3_nhwc(C.byref(d), _stream_ptr()), "esrp_conv3x3_nhwc")
+
+
+def nchw_f32_to_nhwc_bf16(x: torch.Tensor, c_pad: int) -> torch.Tensor:
+    lib = _lib.load()
+    assert x.is_cuda and x.dtype == torch.float32
+    x = x.contiguous()
+    n, c, h, w = x.shape
+    out = torch.empty((n, h, w, c_pad), dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.esrp_nchw_f32_to_nhwc_bf16(x.data_ptr(), out.data_ptr(), n, c, h, w, c_pad, _stream_ptr()),
+               "esrp_nchw_f32_to_nhwc_bf16")
+    return out
+
+
+def nhwc_bf16_to_nchw_f32(x: torch.Tensor, c: int) -> torch.Tensor:
+    lib = _lib.load()
+    assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous()
+    n, h, w, ct = x.shape
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    _lib.check(lib.esrp_nhwc_bf16_to_nchw_f32(x.data_ptr(), out.data_ptr(), n, c, h, w, ct, _stream_ptr()),
+               "esrp_nhwc_bf16_to_nchw_f32")
+    return out
+
+
+def upsample2x_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous()
+    n, h, w, c = x.shape
+    out = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.esrp_upsample2x_nhwc_bf16(x.data_ptr(), out.data_ptr(), n, h, w, c, _stream_ptr()),
+               "esrp_upsample2x_nhwc_bf16")
+    return out

@@ -1,0 +1,405 @@
+// esrp_api.cu — C ABI (include/esrp.h) over the sm_100a kernels: launch logic, TMA tensor-map
+// encoding, weight repacking and the NCHW<->NHWC boundary converters.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/esrp.h"
+#include "conv3x3_tc.cuh"
+#include "esrp_host.h"
+
+namespace esrp {
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+int set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+#define ESRP_CUDA_OK(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess)                                                              \
+      return set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// driver entry point for cuTensorMapEncodeTiled (no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// NHWC bf16 tensor [n,h,w,c_total] viewed as a 4-D TMA tensor (c, x, y, n); box = (kc, bw, bh, 1).
+int make_nhwc_tmap(CUtensorMap* tm, const void* ptr, int n, int h, int w, int c_total, int kc,
+                   int box_w, int box_h) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  cuuint64_t dims[4] = {(cuuint64_t)c_total, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c_total * 2, (cuuint64_t)w * c_total * 2,
+                           (cuuint64_t)h * w * c_total * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMapSwizzle sw = (kc == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error("cuTensorMapEncodeTiled failed (%d) ptr=%p nhwc=(%d,%d,%d,%d) kc=%d box=(%d,%d)",
+                     (int)r, ptr, n, h, w, c_total, kc, box_w, box_h);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv launch
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
+
+static int g_sm_count = 0;
+int sm_count() {
+  if (g_sm_count == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return -1;
+    g_sm_count = prop.multiProcessorCount;
+  }
+  return g_sm_count;
+}
+
+template <int KC, int BN, int MT, bool HALO>
+static int launch_conv(const esrp_conv3x3_t& d, cudaStream_t stream) {
+  using G = ConvGeom<KC, MT, HALO>;
+  constexpr int RB = G::RB;
+  constexpr int W_CHUNK_BYTES = 9 * BN * RB;
+  constexpr int W_AUX_BYTES = BN * RB;
+
+  ConvKParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = d.n; p.h = d.h; p.w = d.w;
+  p.tiles_x = (d.w + G::TW - 1) / G::TW;
+  p.tiles_y = (d.h + kTileH - 1) / kTileH;
+  p.num_tiles = p.tiles_x * p.tiles_y * d.n;
+  p.num_chunks = d.num_chunks;
+  for (int i = 0; i < d.num_chunks; ++i) {
+    p.chunk_src[i] = d.chunk_src[i];
+    p.chunk_c0[i] = d.chunk_c0[i];
+  }
+  p.aux_chunks = d.aux_chunks;
+  p.cout = d.cout;
+  p.w_packed = static_cast<const uint8_t*>(d.w_packed);
+  p.w_aux = static_cast<const uint8_t*>(d.w_aux);
+  p.bias = d.bias;
+  p.act = d.act; p.s0 = d.s0;
+  p.r1 = d.r1; p.r1_is_f32 = d.r1_is_f32; p.r1_ctotal = d.r1_ctotal; p.r1_c0 = d.r1_c0; p.s1 = d.s1;
+  p.r2 = d.r2; p.r2_is_f32 = d.r2_is_f32; p.r2_ctotal = d.r2_ctotal; p.r2_c0 = d.r2_c0; p.s2 = d.s2;
+  p.noise = d.noise; p.sigma = d.sigma; p.seed = d.seed; p.offset = d.offset;
+  p.out_bf16 = static_cast<__nv_bfloat16*>(d.out_bf16); p.ob_ctotal = d.ob_ctotal; p.ob_c0 = d.ob_c0;
+  p.out_f32 = static_cast<float*>(d.out_f32); p.of_ctotal = d.of_ctotal; p.of_c0 = d.of_c0;
+  p.out_nchw = d.out_nchw;
+
+  const bool has_aux = d.aux_chunks > 0;
+  const int bnt = has_aux ? 2 * BN : BN;
+  uint32_t cols = 32;
+  while (cols < static_cast<uint32_t>(2 * MT * bnt)) cols <<= 1;
+  if (cols > 512) return set_error("conv3x3: TMEM budget exceeded (MT=%d BN=%d aux=%d)", MT, BN, has_aux);
+  p.tmem_cols = cols;
+
+  // shared memory plan: 1 KB align slack + 1 KB barriers + [resident weights] + stages
+  const int w_all = d.num_chunks * W_CHUNK_BYTES + d.aux_chunks * W_AUX_BYTES;
+  const int fixed = 2048;
+  int stage_res = G::A_BYTES;
+  int stage_str = G::A_BYTES + W_CHUNK_BYTES + (has_aux ? W_AUX_BYTES : 0);
+  int s_res = (kMaxSmem - fixed - w_all) / stage_res;
+  int s_str = (kMaxSmem - fixed) / stage_str;
+  if (s_res >= 2 || (s_res >= 1 && s_str < 1)) {
+    p.w_resident = 1;
+    p.stages = s_res > 8 ? 8 : s_res;
+  } else {
+    p.w_resident = 0;
+    p.stages = s_str > 8 ? 8 : s_str;
+  }
+  if (p.stages < 1) return set_error("conv3x3: tile does not fit in shared memory (KC=%d BN=%d MT=%d)", KC, BN, MT);
+  const int smem = fixed + (p.w_resident ? w_all : 0) + p.stages * (p.w_resident ? stage_res : stage_str);
+
+  CUtensorMap tm0, tm1;
+  if (make_nhwc_tmap(&tm0, d.src[0], d.n, d.h, d.w, d.src_ctotal[0], KC, G::HW, G::HH)) return 1;
+  if (d.src[1]) {
+    if (make_nhwc_tmap(&tm1, d.src[1], d.n, d.h, d.w, d.src_ctotal[1], KC, G::HW, G::HH)) return 1;
+  } else {
+    tm1 = tm0;
+  }
+
+  auto kern = conv3x3_tc_kernel<KC, BN, MT, HALO>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    ESRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    attr_set = true;
+  }
+  int sms = sm_count();
+  if (sms <= 0) return set_error("conv3x3: no CUDA device");
+  int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  if (grid < 1) return 0;
+  kern<<<grid, kConvThreads, smem, stream>>>(tm0, tm1, p);
+  ESRP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <int KC, int BN>
+static int dispatch_variant(const esrp_conv3x3_t& d, cudaStream_t s) {
+  const bool aligned = d.variant & ESRP_VARIANT_ALIGNED;
+  const bool mt1 = d.variant & ESRP_VARIANT_MT1;
+  if (aligned) return mt1 ? launch_conv<KC, BN, 1, false>(d, s) : launch_conv<KC, BN, 2, false>(d, s);
+  return mt1 ? launch_conv<KC, BN, 1, true>(d, s) : launch_conv<KC, BN, 2, true>(d, s);
+}
+
+static int conv_dispatch(const esrp_conv3x3_t& d, cudaStream_t s) {
+  if (d.n < 1 || d.h < 1 || d.w < 1) return set_error("conv3x3: bad shape n=%d h=%d w=%d", d.n, d.h, d.w);
+  if (d.num_chunks < 1 || d.num_chunks > ESRP_MAX_CHUNKS) return set_error("conv3x3: num_chunks=%d out of range", d.num_chunks);
+  if (d.aux_chunks < 0 || d.aux_chunks > d.num_chunks) return set_error("conv3x3: aux_chunks=%d out of range", d.aux_chunks);
+  if (d.aux_chunks > 0 && !d.w_aux) return set_error("conv3x3: aux_chunks without w_aux");
+  if (!d.src[0] || !d.w_packed) return set_error("conv3x3: null src/weights");
+  if (d.cout < 1 || d.cout > d.bn) return set_error("conv3x3: cout=%d vs bn=%d", d.cout, d.bn);
+  for (int i = 0; i < d.num_chunks; ++i) {
+    int s_ = d.chunk_src[i];
+    if (s_ < 0 || s_ > 1 || !d.src[s_]) return set_error("conv3x3: chunk %d reads missing src %d", i, s_);
+    if (d.chunk_c0[i] < 0 || d.chunk_c0[i] + d.kc > d.src_ctotal[s_] || (d.chunk_c0[i] % 8))
+      return set_error("conv3x3: chunk %d channel range [%d,%d) invalid for src with %d channels", i,
+                       d.chunk_c0[i], d.chunk_c0[i] + d.kc, d.src_ctotal[s_]);
+  }
+  for (int i = 0; i < 2; ++i)
+    if (d.src[i] && (d.src_ctotal[i] % 8)) return set_error("conv3x3: src_ctotal must be a multiple of 8");
+  if (d.out_bf16 && ((d.ob_ctotal % 8) || (d.ob_c0 % 8))) return set_error("conv3x3: out_bf16 channel alignment");
+  if (d.out_f32 && ((d.of_ctotal % 4) || (d.of_c0 % 4))) return set_error("conv3x3: out_f32 channel alignment");
+  if (d.r1 && ((d.r1_ctotal % 8) || (d.r1_c0 % 8))) return set_error("conv3x3: r1 channel alignment");
+  if (d.r2 && ((d.r2_ctotal % 8) || (d.r2_c0 % 8))) return set_error("conv3x3: r2 channel alignment");
+  if ((d.out_bf16 || d.out_f32) && (d.cout % 16)) return set_error("conv3x3: NHWC outputs need cout %% 16 == 0");
+  if (d.kc == 64) {
+    switch (d.bn) {
+      case 16: return dispatch_variant<64, 16>(d, s);
+      case 32: return dispatch_variant<64, 32>(d, s);
+      case 64: return dispatch_variant<64, 64>(d, s);
+    }
+  } else if (d.kc == 32) {
+    switch (d.bn) {
+      case 16: return dispatch_variant<32, 16>(d, s);
+      case 32: return dispatch_variant<32, 32>(d, s);
+      case 64: return dispatch_variant<32, 64>(d, s);
+    }
+  }
+  return set_error("conv3x3: unsupported kc=%d bn=%d (kc in {32,64}, bn in {16,32,64})", d.kc, d.bn);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight repack: OIHW fp32 -> [chunk][tap][bn][kc] bf16, rows pre-swizzled for UMMA/TMA
+// ------------------------------------------------------------------------------------------------
+struct ChunkTable {
+  int lc0[ESRP_MAX_CHUNKS];
+};
+
+__device__ __forceinline__ int swizzled_elem(int row, int k, int kc) {
+  // 16-byte chunk index XOR row bits, matching CU_TENSOR_MAP_SWIZZLE_{128B,64B} / UMMA layouts.
+  const int chunk16 = k >> 3;
+  const int x = (kc == 64) ? (row & 7) : ((row >> 1) & 3);
+  return row * kc + (((chunk16 ^ x) << 3) | (k & 7));
+}
+
+__global__ void pack_conv_weights_kernel(const float* __restrict__ w, int cout, int cin, int taps,
+                                         int kc, int bn, int num_chunks, ChunkTable tab,
+                                         __nv_bfloat16* __restrict__ out) {
+  const int total = num_chunks * taps * bn * kc;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i % kc;
+    const int row = (i / kc) % bn;
+    const int tap = (i / (kc * bn)) % taps;
+    const int chunk = i / (kc * bn * taps);
+    const int ci = tab.lc0[chunk] + k;
+    float v = 0.f;
+    if (row < cout && ci < cin) v = w[(static_cast<size_t>(row) * cin + ci) * taps + tap];
+    out[static_cast<size_t>(chunk * taps + tap) * bn * kc + swizzled_elem(row, k, kc)] = __float2bfloat16_rn(v);
+  }
+}
+
+static int pack_weights(const float* w, int cout, int cin, int taps, int kc, int bn, int num_chunks,
+                        const int32_t* lc0, void* out, cudaStream_t stream) {
+  if (!w || !out || !lc0) return set_error("pack_weights: null pointer");
+  if (kc != 32 && kc != 64) return set_error("pack_weights: kc must be 32 or 64");
+  if (bn % 16 || bn < 16 || bn > 256 || cout > bn) return set_error("pack_weights: bad bn=%d cout=%d", bn, cout);
+  if (num_chunks < 1 || num_chunks > ESRP_MAX_CHUNKS) return set_error("pack_weights: num_chunks=%d", num_chunks);
+  ChunkTable tab;
+  for (int i = 0; i < ESRP_MAX_CHUNKS; ++i) tab.lc0[i] = i < num_chunks ? lc0[i] : 0;
+  const int total = num_chunks * taps * bn * kc;
+  const int threads = 256;
+  int blocks = (total + threads - 1) / threads;
+  if (blocks > 1024) blocks = 1024;
+  pack_conv_weights_kernel<<<blocks, threads, 0, stream>>>(w, cout, cin, taps, kc, bn, num_chunks, tab,
+                                                           static_cast<__nv_bfloat16*>(out));
+  ESRP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// boundary converters (HBM-bound, coalesced on the NHWC side, 32x32 smem transpose tiles)
+// ------------------------------------------------------------------------------------------------
+// NCHW fp32 -> NHWC bf16 with zero channel padding.  One block handles 32 pixels x all channels.
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                    int c, int hw, int c_pad) {
+  extern __shared__ float tile[];  // [c_pad][33]
+  const int img = blockIdx.y;
+  const int p0 = blockIdx.x * 32;
+  const float* s = src + static_cast<size_t>(img) * c * hw;
+  for (int i = threadIdx.x; i < c_pad * 32; i += blockDim.x) {
+    const int ch = i / 32, px = i % 32;
+    float v = 0.f;
+    if (ch < c && p0 + px < hw) v = s[static_cast<size_t>(ch) * hw + p0 + px];
+    tile[ch * 33 + px] = v;
+  }
+  __syncthreads();
+  __nv_bfloat16* d = dst + (static_cast<size_t>(img) * hw + p0) * c_pad;
+  for (int i = threadIdx.x; i < c_pad * 32; i += blockDim.x) {
+    const int px = i / c_pad, ch = i % c_pad;
+    if (p0 + px < hw) d[static_cast<size_t>(px) * c_pad + ch] = __float2bfloat16_rn(tile[ch * 33 + px]);
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int c,
+                                    int hw, int c_total) {
+  extern __shared__ float tile[];  // [c][33]
+  const int img = blockIdx.y;
+  const int p0 = blockIdx.x * 32;
+  const __nv_bfloat16* s = src + (static_cast<size_t>(img) * hw + p0) * c_total;
+  for (int i = threadIdx.x; i < c * 32; i += blockDim.x) {
+    const int px = i / c, ch = i % c;
+    float v = 0.f;
+    if (p0 + px < hw) v = __bfloat162float(s[static_cast<size_t>(px) * c_total + ch]);
+    tile[ch * 33 + px] = v;
+  }
+  __syncthreads();
+  float* d = dst + static_cast<size_t>(img) * c * hw;
+  for (int i = threadIdx.x; i < c * 32; i += blockDim.x) {
+    const int ch = i / 32, px = i % 32;
+    if (p0 + px < hw) d[static_cast<size_t>(ch) * hw + p0 + px] = tile[ch * 33 + px];
+  }
+}
+
+// nearest x2 upsample, NHWC bf16, 16-byte vectors: each thread copies one 8-channel vector to 4 outputs.
+__global__ void upsample2x_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int n, int h,
+                                  int w, int cv) {
+  const size_t total = static_cast<size_t>(n) * h * w * cv;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % cv);
+    size_t t = i / cv;
+    const int x = static_cast<int>(t % w); t /= w;
+    const int y = static_cast<int>(t % h);
+    const int img = static_cast<int>(t / h);
+    const uint4 val = __ldg(src + i);
+    const size_t ow = static_cast<size_t>(2) * w;
+    const size_t base = ((static_cast<size_t>(img) * 2 * h + 2 * y) * ow + 2 * x) * cv + v;
+    dst[base] = val;
+    dst[base + cv] = val;
+    dst[base + ow * cv] = val;
+    dst[base + ow * cv + cv] = val;
+  }
+}
+
+}  // namespace esrp
+
+// ================================================================================================
+// extern "C"
+// ================================================================================================
+using namespace esrp;
+
+extern "C" {
+
+const char* esrp_last_error(void) { return g_err; }
+int esrp_version(void) { return 100; }
+int esrp_sm_count(void) { return sm_count(); }
+
+int esrp_conv3x3_nhwc(const esrp_conv3x3_t* desc, void* stream) {
+  if (!desc) return set_error("esrp_conv3x3_nhwc: null desc");
+  return conv_dispatch(*desc, static_cast<cudaStream_t>(stream));
+}
+
+int64_t esrp_packed_conv3x3_bytes(int32_t num_chunks, int32_t kc, int32_t bn) {
+  return static_cast<int64_t>(num_chunks) * 9 * bn * kc * 2;
+}
+int64_t esrp_packed_conv1x1_bytes(int32_t num_chunks, int32_t kc, int32_t bn) {
+  return static_cast<int64_t>(num_chunks) * bn * kc * 2;
+}
+
+int esrp_pack_conv3x3_weights(const float* w_oihw, int32_t cout, int32_t cin, int32_t kc, int32_t bn,
+                              int32_t num_chunks, const int32_t* chunk_lc0_host, void* out, void* stream) {
+  return pack_weights(w_oihw, cout, cin, 9, kc, bn, num_chunks, chunk_lc0_host, out,
+                      static_cast<cudaStream_t>(stream));
+}
+int esrp_pack_conv1x1_weights(const float* w_oi, int32_t cout, int32_t cin, int32_t kc, int32_t bn,
+                              int32_t num_chunks, const int32_t* chunk_lc0_host, void* out, void* stream) {
+  return pack_weights(w_oi, cout, cin, 1, kc, bn, num_chunks, chunk_lc0_host, out,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int esrp_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int32_t n, int32_t c, int32_t h, int32_t w,
+                               int32_t c_pad, void* stream) {
+  if (!src || !dst || c_pad < c || c_pad > 256) return set_error("nchw_to_nhwc: bad arguments");
+  const int hw = h * w;
+  dim3 grid((hw + 31) / 32, n);
+  nchw_to_nhwc_kernel<<<grid, 256, c_pad * 33 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), c, hw, c_pad);
+  ESRP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int esrp_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int32_t n, int32_t c, int32_t h, int32_t w,
+                               int32_t c_total, void* stream) {
+  if (!src || !dst || c_total < c || c > 256) return set_error("nhwc_to_nchw: bad arguments");
+  const int hw = h * w;
+  dim3 grid((hw + 31) / 32, n);
+  nhwc_to_nchw_kernel<<<grid, 256, c * 33 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), dst, c, hw, c_total);
+  ESRP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int esrp_upsample2x_nhwc_bf16(const void* src, void* dst, int32_t n, int32_t h, int32_t w, int32_t c,
+                              void* stream) {
+  if (!src || !dst || (c % 8)) return set_error("upsample2x: c must be a multiple of 8");
+  const int cv = c / 8;
+  const size_t total = static_cast<size_t>(n) * h * w * cv;
+  int blocks = static_cast<int>((total + 255) / 256);
+  const int cap = 148 * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) return 0;
+  upsample2x_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(src), static_cast<uint4*>(dst), n, h, w, cv);
+  ESRP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+/* esrp.h — C ABI of libesrp.so, the B200-native (sm_100a) hot path of ESRGAN+/nESRGAN+.
+ *
+ * The reference (ncarraz/ESRGANplus) has no FFI: its hot path is the Python nn.Module surface
+ *   codes/models/modules/architecture.py:47-78   (RRDBNet)
+ *   codes/models/modules/architecture.py:87-129  (Discriminator_VGG_128)
+ *   codes/models/modules/block.py:232-291        (ResidualDenseBlock_5C, RRDB, GaussianNoise)
+ *   test_image/architecture.py:7-38              (RRDB_Net)
+ * whose forward() dispatches to torch.nn.Conv2d / LeakyReLU / cat / add.  This library is what a
+ * maintainer binds *beneath* those classes (ctypes stub in INTEGRATION.md): plain pointers and
+ * sizes, no torch types.  All pointers are DEVICE pointers unless a name says host; all tensors
+ * are borrowed (caller owns memory); every call is asynchronous on `stream` (a cudaStream_t
+ * passed as void*).  Every function returns 0 on success, non-zero on error;
+ * esrp_last_error() returns a thread-local message.
+ *
+ * Data layout in HBM: activations NHWC bf16 (optionally with an fp32 NHWC twin for the residual
+ * trunk), weights repacked from the reference's OIHW fp32 wire format into K-major, pre-swizzled
+ * bf16 tiles (derived cache; never stored in a state_dict).
+ */
+#ifndef ESRP_H_
+#define ESRP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESRP_MAX_CHUNKS 8
+
+/* Kernel variant bits for esrp_conv3x3_t.variant (0 = library default). */
+#define ESRP_VARIANT_ALIGNED 1 /* 3 per-kx TMA boxes, atom-aligned UMMA operands (debug/safe)  */
+#define ESRP_VARIANT_MT1 2     /* one 16x8-pixel UMMA M-tile per CTA tile instead of two       */
+
+/* One fused 3x3 / stride-1 / zero-pad-1 convolution over NHWC bf16 activations.
+ * Replaces one `conv_block` call plus the torch.cat that feeds it and the elementwise ops that
+ * follow it in block.py:260-268 / 287-291 and architecture.py:55-71:
+ *
+ *   acc  = sum_{chunk,tap} W[chunk][tap] . src[chunk_src][.., chunk_c0 : chunk_c0+kc]
+ *   aux  = sum_{chunk<aux_chunks} Waux[chunk] . src (centre tap only)            (conv1x1, :263)
+ *   v    = s0 * act(acc + bias) + aux + s1 * r1                                   (:262-268)
+ *   v    = v * (1 + sigma * N(0,1))           if noise                            (:117-121)
+ *   v    = s2 * v + r2                        if r2                               (:291)
+ *   out_* <- v
+ */
+typedef struct esrp_conv3x3 {
+  int32_t n, h, w;              /* batch, height, width (output == input spatial size)       */
+  const void* src[2];           /* up to two NHWC bf16 source tensors [n,h,w,src_ctotal[i]]  */
+  int32_t src_ctotal[2];        /* channels of each allocation (multiple of 8)               */
+  int32_t kc;                   /* K-chunk width in channels: 32 or 64                       */
+  int32_t num_chunks;           /* K = 9 * kc * num_chunks                                   */
+  int32_t chunk_src[ESRP_MAX_CHUNKS]; /* which src each chunk reads                         */
+  int32_t chunk_c0[ESRP_MAX_CHUNKS];  /* first channel of the chunk in that src             */
+  int32_t aux_chunks;           /* leading chunks that also feed the 1x1 aux accumulator     */
+  int32_t bn;                   /* padded Cout = UMMA N: 16, 32 or 64                        */
+  int32_t cout;                 /* real Cout <= bn                                           */
+  const void* w_packed;         /* from esrp_pack_conv3x3_weights                            */
+  const void* w_aux;            /* from esrp_pack_conv1x1_weights, or NULL                   */
+  const float* bias;            /* [bn] fp32 (zero padded), or NULL                          */
+  int32_t act;                  /* 0 none, 1 LeakyReLU(0.2)                                  */
+  float s0;
+  const void* r1;               /* residual 1, NHWC [n,h,w,r1_ctotal], read at r1_c0..       */
+  int32_t r1_is_f32, r1_ctotal, r1_c0;
+  float s1;
+  const void* r2;               /* residual 2 (RRDB level)                                   */
+  int32_t r2_is_f32, r2_ctotal, r2_c0;
+  float s2;
+  int32_t noise;                /* 1: multiplicative Gaussian noise (train mode)             */
+  float sigma;
+  uint64_t seed, offset;        /* Philox key / per-call counter offset                      */
+  void* out_bf16;               /* NHWC bf16 [n,h,w,ob_ctotal] written at ob_c0.. or NULL    */
+  int32_t ob_ctotal, ob_c0;
+  void* out_f32;                /* NHWC fp32 twin, or NULL                                   */
+  int32_t of_ctotal, of_c0;
+  float* out_nchw;              /* NCHW fp32 [n,cout,h,w], or NULL                           */
+  int32_t variant;              /* ESRP_VARIANT_* bits                                       */
+} esrp_conv3x3_t;
+
+const char* esrp_last_error(void);
+int esrp_version(void);
+
+/* Device/SM query: returns the SM count of the current device, or -1. */
+int esrp_sm_count(void);
+
+int esrp_conv3x3_nhwc(const esrp_conv3x3_t* desc, void* stream);
+
+/* Packed size in bytes of the weights for (num_chunks, kc, bn). */
+int64_t esrp_packed_conv3x3_bytes(int32_t num_chunks, int32_t kc, int32_t bn);
+int64_t esrp_packed_conv1x1_bytes(int32_t num_chunks, int32_t kc, int32_t bn);
+
+/* Repack reference-format weights (OIHW fp32, device) into UMMA B tiles.
+ * chunk_lc0[i] = first *logical* input channel (index into dim 1 of w_oihw) of chunk i;
+ * channels >= cin and rows >= cout are zero-filled. */
+int esrp_pack_conv3x3_weights(const float* w_oihw, int32_t cout, int32_t cin, int32_t kc,
+                              int32_t bn, int32_t num_chunks, const int32_t* chunk_lc0_host,
+                              void* out, void* stream);
+int esrp_pack_conv1x1_weights(const float* w_oi, int32_t cout, int32_t cin, int32_t kc, int32_t bn,
+                              int32_t num_chunks, const int32_t* chunk_lc0_host, void* out,
+                              void* stream);
+
+/* Boundary layout converters (reference tensors are NCHW fp32, test_image/test.py:31-35). */
+int esrp_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int32_t n, int32_t c, int32_t h,
+                               int32_t w, int32_t c_pad, void* stream);
+int esrp_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int32_t n, int32_t c, int32_t h,
+                               int32_t w, int32_t c_total, void* stream);
+/* nn.Upsample(scale_factor=2, mode='nearest') on NHWC bf16 (block.py:319). */
+int esrp_upsample2x_nhwc_bf16(const void* src, void* dst, int32_t n, int32_t h, int32_t w,
+                              int32_t c, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESRP_H_ */
