@@ -59,6 +59,8 @@ SYMBOLS = {
     "esrp_last_error": (C.c_char_p, []),
     "esrp_version": (C.c_int, []),
     "esrp_sm_count": (C.c_int, []),
+    "esrp_sizeof_conv3x3": (C.c_int32, []),
+    "esrp_philox_normal_host": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p]),
     "esrp_conv3x3_nhwc": (C.c_int, [C.POINTER(Conv3x3Desc), C.c_void_p]),
     "esrp_packed_conv3x3_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "esrp_packed_conv1x1_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
@@ -72,6 +74,17 @@ SYMBOLS = {
                                              C.c_int32, C.c_int32, C.c_void_p]),
     "esrp_upsample2x_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                             C.c_int32, C.c_void_p]),
+    "esrp_rrdbnet_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.POINTER(C.c_void_p)]),
+    "esrp_rrdbnet_destroy": (None, [C.c_void_p]),
+    "esrp_rrdbnet_num_tensors": (C.c_int32, [C.c_void_p]),
+    "esrp_rrdbnet_tensor_key": (C.c_char_p, [C.c_void_p, C.c_int32]),
+    "esrp_rrdbnet_tensor_shape": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
+    "esrp_rrdbnet_load_weights": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
+    "esrp_rrdbnet_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    "esrp_rrdbnet_num_launches": (C.c_int32, [C.c_void_p]),
+    "esrp_rrdbnet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,143 @@
+"""Drop-in network classes: same constructor signatures, module tree and state_dict keys as the
+reference's ``codes/models/modules/architecture.py`` (RRDBNet :47-78, Discriminator_VGG_128 :87-129)
+and ``test_image/architecture.py`` (RRDB_Net :7-38), with ``forward`` executed by the hand-written
+sm_100a kernels in libesrp.so instead of nn.Conv2d / torch.cat / elementwise ATen ops.
+
+``networks.define_G`` / ``define_D`` (networks.py:96-99,117-119), ``train.py``, ``test.py`` and
+``test_image/test.py`` bind to these names; see INTEGRATION.md for the two-line shim.
+
+There is no torch-math or CPU fallback: inputs must be CUDA fp32 NCHW tensors, and a missing
+libesrp.so raises at the first forward.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import block as B
+
+
+def _flat(*groups) -> nn.Sequential:
+    """Concatenate module lists into ONE nn.Sequential: the flat indices are what produce the
+    reference's key numbers (model.0/1/3/6/8/10, features.0/2/3/5/6/...; block.py:95-108)."""
+    mods: List[nn.Module] = []
+    for g in groups:
+        mods.extend(g if isinstance(g, (list, tuple)) else [g])
+    return nn.Sequential(*mods)
+
+
+class _GeneratorBase(nn.Module):
+    def _build(self, in_nc, out_nc, nf, nb, gc, upscale, norm_type, act_type, mode, upsample_mode, rrdb_noise):
+        if upsample_mode not in ("upconv", "pixelshuffle"):
+            raise NotImplementedError("upsample mode [{:s}] is not found".format(upsample_mode))
+        if upsample_mode != "upconv" or upscale == 3 or norm_type or (act_type or "").lower() != "leakyrelu":
+            # accepted by the reference's signature but never selected by the ESRGAN+/nESRGAN+ configs
+            # (options/train/train_ESRGANplus.json, test_image/test.py:15-16); no kernels exist for them
+            raise NotImplementedError(
+                "esrganplus_b200 implements the ESRGAN+ hot path only: upsample_mode='upconv', "
+                "upscale in {1,2,4}, norm_type=None, act_type='leakyrelu'")
+        n_up = int(math.log(upscale, 2))
+        if 2 ** n_up != upscale:
+            raise NotImplementedError(f"upscale={upscale} unsupported")
+        # architecture.py:56 passes the literal gc=32 to every RRDB whatever `gc` says; keep that.
+        self.cfg = dict(in_nc=in_nc, out_nc=out_nc, nf=nf, nb=nb, gc=32, upscale=upscale)
+        trunk = nn.Sequential(*[B.RRDB(nf, 3, 32, 1, True, "zero", None, act_type, "CNA", rrdb_noise=rrdb_noise)
+                                for _ in range(nb)],
+                              *B.layer_group(nf, nf, 3))                       # LR_conv, no act (:58)
+        ups = []
+        for _ in range(n_up):                                                   # block.py:315-322
+            ups += [nn.Upsample(scale_factor=2, mode="nearest")] + B.layer_group(nf, nf, 3, act_type=act_type)
+        self.model = _flat(B.layer_group(in_nc, nf, 3),                         # fea_conv (:55)
+                           B.ShortcutBlock(trunk), ups,
+                           B.layer_group(nf, nf, 3, act_type=act_type),         # HR_conv0 (:70)
+                           B.layer_group(nf, out_nc, 3))                        # HR_conv1 (:71)
+        # native engines, one per device; kept out of the module/state machinery on purpose
+        object.__setattr__(self, "_engines", {})
+        object.__setattr__(self, "_step", 0)
+
+    # -- engine plumbing -----------------------------------------------------------------------
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st["_engines"] = {}
+        return st
+
+    def _engine_for(self, device: torch.device):
+        from .engine import GeneratorEngine
+        eng = self._engines.get(device)
+        if eng is None:
+            c = self.cfg
+            eng = GeneratorEngine(c["in_nc"], c["out_nc"], c["nf"], c["nb"], c["gc"], c["upscale"], device)
+            self._engines[device] = eng
+        return eng
+
+    def noise_seed(self) -> int:
+        """Philox key for this forward: torch's global seed mixed with a per-module call counter, so
+        `torch.manual_seed` reproduces a training run (the reference draws from the global stream)."""
+        object.__setattr__(self, "_step", self._step + 1)
+        return (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._step) & 0xFFFFFFFFFFFFFFFF
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError("esrganplus_b200.RRDBNet runs on CUDA (sm_100a) only; there is no CPU path "
+                               "(use the reference modules for CPU inference)")
+        params: Dict[str, torch.Tensor] = dict(self.named_parameters())
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params.values()))
+        if needs_grad:
+            from .autograd import generator_apply
+            return generator_apply(self, x, params)
+        eng = self._engine_for(x.device)
+        eng.sync_weights(params)
+        return eng.forward(x, self.training, self.noise_seed() if self.training else 0)
+
+
+class RRDBNet(_GeneratorBase):
+    """architecture.py:47-78.  RRDBNet(in_nc, out_nc, nf, nb, gc=32, upscale=4, norm_type=None,
+    act_type='leakyrelu', mode='CNA', upsample_mode='upconv')."""
+
+    def __init__(self, in_nc, out_nc, nf, nb, gc=32, upscale=4, norm_type=None, act_type="leakyrelu",
+                 mode="CNA", upsample_mode="upconv"):
+        super().__init__()
+        self._build(in_nc, out_nc, nf, nb, gc, upscale, norm_type, act_type, mode, upsample_mode, rrdb_noise=False)
+
+
+class RRDB_Net(_GeneratorBase):
+    """test_image/architecture.py:7-38 — the standalone inference copy (extra, unused `res_scale`;
+    its RRDB carries a second, parameter-free GaussianNoise that is the identity in eval())."""
+
+    def __init__(self, in_nc, out_nc, nf, nb, gc=32, upscale=4, norm_type=None, act_type="leakyrelu",
+                 mode="CNA", res_scale=1, upsample_mode="upconv"):
+        super().__init__()
+        self._build(in_nc, out_nc, nf, nb, gc, upscale, norm_type, act_type, mode, upsample_mode, rrdb_noise=True)
+
+    def forward(self, x):
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("RRDB_Net is the inference copy (test_image/test.py); train with RRDBNet")
+        return super().forward(x)
+
+
+class Discriminator_VGG_128(nn.Module):
+    """architecture.py:87-129.  Ten conv layers (k3 s1 / k4 s2 alternating, BatchNorm2d from the second
+    on, LeakyReLU 0.2) 128x128 -> 4x4, then Linear(8192,100) + LeakyReLU + Linear(100,1)."""
+
+    def __init__(self, in_nc, base_nf, norm_type="batch", act_type="leakyrelu", mode="CNA"):
+        super().__init__()
+        if mode != "CNA":
+            raise NotImplementedError("Discriminator_VGG_128: only mode='CNA' is on the hot path")
+        nf = base_nf
+        plan = [(in_nc, nf, 3, 1, None), (nf, nf, 4, 2, norm_type),
+                (nf, 2 * nf, 3, 1, norm_type), (2 * nf, 2 * nf, 4, 2, norm_type),
+                (2 * nf, 4 * nf, 3, 1, norm_type), (4 * nf, 4 * nf, 4, 2, norm_type),
+                (4 * nf, 8 * nf, 3, 1, norm_type), (8 * nf, 8 * nf, 4, 2, norm_type),
+                (8 * nf, 8 * nf, 3, 1, norm_type), (8 * nf, 8 * nf, 4, 2, norm_type)]
+        self.features = _flat(*[B.layer_group(ci, co, k, s, norm_type=nt, act_type=act_type)
+                                for ci, co, k, s, nt in plan])
+        self.classifier = nn.Sequential(nn.Linear(512 * 4 * 4, 100), nn.LeakyReLU(0.2, True), nn.Linear(100, 1))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError("esrganplus_b200.Discriminator_VGG_128 runs on CUDA (sm_100a) only")
+        from .discriminator import discriminator_apply
+        return discriminator_apply(self, x)

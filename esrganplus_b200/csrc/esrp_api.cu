@@ -28,13 +28,6 @@ int set_error(const char* fmt, ...) {
   return 1;
 }
 
-#define ESRP_CUDA_OK(expr)                                                              \
-  do {                                                                                  \
-    cudaError_t _e = (expr);                                                            \
-    if (_e != cudaSuccess)                                                              \
-      return set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
-  } while (0)
-
 // ------------------------------------------------------------------------------------------------
 // driver entry point for cuTensorMapEncodeTiled (no link-time dependency on libcuda)
 // ------------------------------------------------------------------------------------------------
@@ -94,13 +87,13 @@ int sm_count() {
 }
 
 template <int KC, int BN, int MT, bool HALO>
-static int launch_conv(const esrp_conv3x3_t& d, cudaStream_t stream) {
+static int plan_conv_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
   using G = ConvGeom<KC, MT, HALO>;
   constexpr int RB = G::RB;
   constexpr int W_CHUNK_BYTES = 9 * BN * RB;
   constexpr int W_AUX_BYTES = BN * RB;
 
-  ConvKParams p;
+  ConvKParams& p = out->params;
   memset(&p, 0, sizeof(p));
   p.n = d.n; p.h = d.h; p.w = d.w;
   p.tiles_x = (d.w + G::TW - 1) / G::TW;
@@ -146,14 +139,13 @@ static int launch_conv(const esrp_conv3x3_t& d, cudaStream_t stream) {
     p.stages = s_str > 8 ? 8 : s_str;
   }
   if (p.stages < 1) return set_error("conv3x3: tile does not fit in shared memory (KC=%d BN=%d MT=%d)", KC, BN, MT);
-  const int smem = fixed + (p.w_resident ? w_all : 0) + p.stages * (p.w_resident ? stage_res : stage_str);
+  out->smem = fixed + (p.w_resident ? w_all : 0) + p.stages * (p.w_resident ? stage_res : stage_str);
 
-  CUtensorMap tm0, tm1;
-  if (make_nhwc_tmap(&tm0, d.src[0], d.n, d.h, d.w, d.src_ctotal[0], KC, G::HW, G::HH)) return 1;
+  if (make_nhwc_tmap(&out->tm0, d.src[0], d.n, d.h, d.w, d.src_ctotal[0], KC, G::HW, G::HH)) return 1;
   if (d.src[1]) {
-    if (make_nhwc_tmap(&tm1, d.src[1], d.n, d.h, d.w, d.src_ctotal[1], KC, G::HW, G::HH)) return 1;
+    if (make_nhwc_tmap(&out->tm1, d.src[1], d.n, d.h, d.w, d.src_ctotal[1], KC, G::HW, G::HH)) return 1;
   } else {
-    tm1 = tm0;
+    out->tm1 = out->tm0;
   }
 
   auto kern = conv3x3_tc_kernel<KC, BN, MT, HALO>;
@@ -162,24 +154,30 @@ static int launch_conv(const esrp_conv3x3_t& d, cudaStream_t stream) {
     ESRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     attr_set = true;
   }
+  out->kernel = reinterpret_cast<const void*>(kern);
   int sms = sm_count();
   if (sms <= 0) return set_error("conv3x3: no CUDA device");
-  int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  if (grid < 1) return 0;
-  kern<<<grid, kConvThreads, smem, stream>>>(tm0, tm1, p);
-  ESRP_CUDA_OK(cudaGetLastError());
+  out->grid = p.num_tiles < sms ? p.num_tiles : sms;
+  return 0;
+}
+
+int run_conv(const ConvLaunch& L, cudaStream_t stream) {
+  if (L.grid < 1) return 0;
+  void* args[3] = {const_cast<CUtensorMap*>(&L.tm0), const_cast<CUtensorMap*>(&L.tm1),
+                   const_cast<ConvKParams*>(&L.params)};
+  ESRP_CUDA_OK(cudaLaunchKernel(L.kernel, dim3(L.grid), dim3(kConvThreads), args, L.smem, stream));
   return 0;
 }
 
 template <int KC, int BN>
-static int dispatch_variant(const esrp_conv3x3_t& d, cudaStream_t s) {
+static int dispatch_variant(const esrp_conv3x3_t& d, ConvLaunch* out) {
   const bool aligned = d.variant & ESRP_VARIANT_ALIGNED;
   const bool mt1 = d.variant & ESRP_VARIANT_MT1;
-  if (aligned) return mt1 ? launch_conv<KC, BN, 1, false>(d, s) : launch_conv<KC, BN, 2, false>(d, s);
-  return mt1 ? launch_conv<KC, BN, 1, true>(d, s) : launch_conv<KC, BN, 2, true>(d, s);
+  if (aligned) return mt1 ? plan_conv_t<KC, BN, 1, false>(d, out) : plan_conv_t<KC, BN, 2, false>(d, out);
+  return mt1 ? plan_conv_t<KC, BN, 1, true>(d, out) : plan_conv_t<KC, BN, 2, true>(d, out);
 }
 
-static int conv_dispatch(const esrp_conv3x3_t& d, cudaStream_t s) {
+int plan_conv(const esrp_conv3x3_t& d, ConvLaunch* out) {
   if (d.n < 1 || d.h < 1 || d.w < 1) return set_error("conv3x3: bad shape n=%d h=%d w=%d", d.n, d.h, d.w);
   if (d.num_chunks < 1 || d.num_chunks > ESRP_MAX_CHUNKS) return set_error("conv3x3: num_chunks=%d out of range", d.num_chunks);
   if (d.aux_chunks < 0 || d.aux_chunks > d.num_chunks) return set_error("conv3x3: aux_chunks=%d out of range", d.aux_chunks);
@@ -202,15 +200,15 @@ static int conv_dispatch(const esrp_conv3x3_t& d, cudaStream_t s) {
   if ((d.out_bf16 || d.out_f32) && (d.cout % 16)) return set_error("conv3x3: NHWC outputs need cout %% 16 == 0");
   if (d.kc == 64) {
     switch (d.bn) {
-      case 16: return dispatch_variant<64, 16>(d, s);
-      case 32: return dispatch_variant<64, 32>(d, s);
-      case 64: return dispatch_variant<64, 64>(d, s);
+      case 16: return dispatch_variant<64, 16>(d, out);
+      case 32: return dispatch_variant<64, 32>(d, out);
+      case 64: return dispatch_variant<64, 64>(d, out);
     }
   } else if (d.kc == 32) {
     switch (d.bn) {
-      case 16: return dispatch_variant<32, 16>(d, s);
-      case 32: return dispatch_variant<32, 32>(d, s);
-      case 64: return dispatch_variant<32, 64>(d, s);
+      case 16: return dispatch_variant<32, 16>(d, out);
+      case 32: return dispatch_variant<32, 32>(d, out);
+      case 64: return dispatch_variant<32, 64>(d, out);
     }
   }
   return set_error("conv3x3: unsupported kc=%d bn=%d (kc in {32,64}, bn in {16,32,64})", d.kc, d.bn);
@@ -341,10 +339,23 @@ extern "C" {
 const char* esrp_last_error(void) { return g_err; }
 int esrp_version(void) { return 100; }
 int esrp_sm_count(void) { return sm_count(); }
+int32_t esrp_sizeof_conv3x3(void) { return static_cast<int32_t>(sizeof(esrp_conv3x3_t)); }
+
+int esrp_philox_normal_host(uint64_t seed, uint64_t offset, int64_t count, float* out_host) {
+  if (!out_host || count < 0) return set_error("philox_normal_host: bad arguments");
+  for (int64_t e = 0; e < count; e += 4) {
+    float z[4];
+    philox_normal4(seed, offset + static_cast<unsigned long long>(e / 4), z);
+    for (int j = 0; j < 4 && e + j < count; ++j) out_host[e + j] = z[j];
+  }
+  return 0;
+}
 
 int esrp_conv3x3_nhwc(const esrp_conv3x3_t* desc, void* stream) {
   if (!desc) return set_error("esrp_conv3x3_nhwc: null desc");
-  return conv_dispatch(*desc, static_cast<cudaStream_t>(stream));
+  ConvLaunch L;
+  if (plan_conv(*desc, &L)) return 1;
+  return run_conv(L, static_cast<cudaStream_t>(stream));
 }
 
 int64_t esrp_packed_conv3x3_bytes(int32_t num_chunks, int32_t kc, int32_t bn) {

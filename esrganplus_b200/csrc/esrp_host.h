@@ -3,6 +3,9 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include "../../include/esrp.h"
+#include "conv_params.h"
+
 namespace esrp {
 // printf-style; stores a thread-local message for esrp_last_error() and returns 1.
 int set_error(const char* fmt, ...);
@@ -10,4 +13,24 @@ int set_error(const char* fmt, ...);
 int make_nhwc_tmap(CUtensorMap* tm, const void* ptr, int n, int h, int w, int c_total, int kc,
                    int box_w, int box_h);
 int sm_count();
+
+// A fully planned conv launch: kernel instantiation, TMA maps, parameters.  Planning (argument
+// validation, tensor-map encoding, shared-memory/TMEM budgeting) happens once per shape; replay is
+// a single cudaLaunchKernel, so a whole-network forward is a flat list of these.
+struct ConvLaunch {
+  const void* kernel = nullptr;
+  CUtensorMap tm0, tm1;
+  ConvKParams params;
+  int grid = 0;
+  int smem = 0;
+};
+int plan_conv(const esrp_conv3x3_t& d, ConvLaunch* out);
+int run_conv(const ConvLaunch& L, cudaStream_t stream);
+
+#define ESRP_CUDA_OK(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess)                                                              \
+      return ::esrp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
 }  // namespace esrp

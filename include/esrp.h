@@ -77,6 +77,13 @@ typedef struct esrp_conv3x3 {
 
 const char* esrp_last_error(void);
 int esrp_version(void);
+/* sizeof(esrp_conv3x3_t) as compiled into the library (binding self-check). */
+int32_t esrp_sizeof_conv3x3(void);
+/* HOST helper: the N(0,1) samples the noise epilogue draws, for element indices [0,count) of a
+ * conv whose Philox key/offset are (seed, offset): element e = pixel*cout + channel (NHWC order)
+ * uses counter offset + e/4, lane e%4.  out_host is a host pointer.  Lets a caller reproduce the
+ * GaussianNoise draw (block.py:120) outside the kernel; the engine uses offset = rdb_index << 36. */
+int esrp_philox_normal_host(uint64_t seed, uint64_t offset, int64_t count, float* out_host);
 
 /* Device/SM query: returns the SM count of the current device, or -1. */
 int esrp_sm_count(void);
@@ -105,6 +112,39 @@ int esrp_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int32_t n, int32_t c
 /* nn.Upsample(scale_factor=2, mode='nearest') on NHWC bf16 (block.py:319). */
 int esrp_upsample2x_nhwc_bf16(const void* src, void* dst, int32_t n, int32_t h, int32_t w,
                               int32_t c, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * RRDBNet generator engine: what RRDBNet.forward / RRDB_Net.forward binds to
+ * (architecture.py:76-78, test_image/architecture.py:36-38).  The handle owns the packed bf16
+ * weight cache and per-shape launch plans; activations live in the caller's workspace.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct esrp_rrdbnet esrp_rrdbnet_t;
+
+/* Mirrors RRDBNet(in_nc, out_nc, nf, nb, gc=32, upscale=4, norm_type=None, act_type='leakyrelu',
+ * mode='CNA', upsample_mode='upconv') (architecture.py:48-49).  Supported: nf in {32,64}, gc=32,
+ * upscale in {1,2,4}; anything else returns an error (no fallback). */
+int esrp_rrdbnet_create(int32_t in_nc, int32_t out_nc, int32_t nf, int32_t nb, int32_t gc,
+                        int32_t upscale, esrp_rrdbnet_t** out);
+void esrp_rrdbnet_destroy(esrp_rrdbnet_t* h);
+/* The state_dict tensors the engine consumes, in reference order, with their key names
+ * ("model.0.weight", "model.1.sub.0.RDB1.conv1x1.weight", ...) and OIHW shapes. */
+int32_t esrp_rrdbnet_num_tensors(const esrp_rrdbnet_t* h);
+const char* esrp_rrdbnet_tensor_key(const esrp_rrdbnet_t* h, int32_t idx);
+int esrp_rrdbnet_tensor_shape(const esrp_rrdbnet_t* h, int32_t idx, int32_t* dims4);
+/* (Re)build the packed weight cache from fp32 device tensors; ptrs is a HOST array of `count`
+ * DEVICE pointers ordered like esrp_rrdbnet_tensor_key.  Call after load_state_dict and after
+ * every optimizer step. */
+int esrp_rrdbnet_load_weights(esrp_rrdbnet_t* h, const void* const* ptrs, int32_t count, void* stream);
+int64_t esrp_rrdbnet_workspace_bytes(const esrp_rrdbnet_t* h, int32_t n, int32_t hgt, int32_t w);
+/* Kernel launches in the most recently planned forward (for bench.py's gpu_launches). */
+int32_t esrp_rrdbnet_num_launches(const esrp_rrdbnet_t* h);
+/* x: NCHW fp32 [n,in_nc,h,w] -> y: NCHW fp32 [n,out_nc,upscale*h,upscale*w] (unclamped, like the
+ * reference).  training!=0 enables the per-RDB multiplicative Gaussian noise (block.py:117-121)
+ * drawn from Philox(seed).  workspace: 1024-byte aligned device memory of at least
+ * esrp_rrdbnet_workspace_bytes(). */
+int esrp_rrdbnet_forward(esrp_rrdbnet_t* h, const float* x, float* y, int32_t n, int32_t hgt, int32_t w,
+                         void* workspace, int64_t workspace_bytes, int32_t training, uint64_t seed,
+                         void* stream);
 
 #ifdef __cplusplus
 }

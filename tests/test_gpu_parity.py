@@ -1,0 +1,258 @@
+"""Parity of the sm_100a path (through the C ABI in libesrp.so) with the oracle and with the golden
+fixtures generated from the reference.
+
+Stated tolerances (DESIGN.md "Precision contract"): operands are rounded to bf16, products are
+accumulated in fp32 in tensor memory, the residual trunk is carried in fp32.
+  * one conv vs torch fp32 conv2d on the SAME bf16-rounded operands: fp32 outputs within
+    2e-3 * max|ref| (accumulation order only), bf16 outputs within 1e-2 * max|ref| (one rounding).
+  * whole networks vs the fp32 reference: max|d| <= 3e-2 * std(ref) and PSNR >= 45 dB on the
+    clamped [0,1] image (utils/util.py:107-114); the 8-bit PNG quantisation floor is 58.9 dB.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import esrganplus_b200 as E
+from esrganplus_b200 import _lib
+from esrganplus_b200 import conv as K
+from oracle import esrgan_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+NET_REL_TOL = 3e-2
+NET_PSNR_DB = 45.0
+
+
+def _golden(golden_dir, name):
+    return dict(np.load(os.path.join(golden_dir, name), allow_pickle=False))
+
+
+def _net_close(y: torch.Tensor, ref: torch.Tensor, what=""):
+    assert y.shape == ref.shape, (y.shape, ref.shape)
+    assert torch.isfinite(y).all(), what
+    err = (y - ref).abs().max().item()
+    rel = err / ref.std().item()
+    psnr = O.psnr_255(y, ref)
+    assert rel <= NET_REL_TOL and psnr >= NET_PSNR_DB, f"{what}: max|d|={err:.3e} rel={rel:.3e} psnr={psnr:.1f}"
+    return rel, psnr
+
+
+def test_extension_is_loaded_and_device_is_blackwell(cuda_dev):
+    lib = _lib.load()
+    assert lib.esrp_sm_count() > 0
+    major, _ = torch.cuda.get_device_capability(cuda_dev)
+    assert major == 10, "kernels are built for sm_100a only"
+
+
+# ---------------------------------------------------------------------------------------------------
+# one conv launch
+# ---------------------------------------------------------------------------------------------------
+def _ref_conv(srcs, chunks, kc, w, bias, act):
+    x = torch.cat([srcs[si][..., c0:c0 + kc] for si, c0 in chunks], dim=3).float().permute(0, 3, 1, 2)
+    y = F.conv2d(x.contiguous(), w.to(torch.bfloat16).float(), bias, padding=1)
+    return F.leaky_relu(y, 0.2) if act else y
+
+
+@pytest.mark.parametrize("variant", [0, _lib.VARIANT_MT1, _lib.VARIANT_ALIGNED])
+@pytest.mark.parametrize("kc,bn", [(64, 32), (64, 64), (32, 32), (32, 64), (64, 16), (32, 16)])
+@pytest.mark.parametrize("shape", [(2, 20, 27), (1, 16, 16), (3, 5, 7), (1, 33, 130)])
+def test_conv3x3_plain(cuda_dev, kc, bn, variant, shape):
+    torch.backends.cudnn.allow_tf32 = False
+    n, h, w = shape
+    g = torch.Generator(device=cuda_dev).manual_seed(kc * 1000 + bn * 10 + variant + h)
+    s0 = torch.randn(n, h, w, 64, device=cuda_dev, generator=g).to(torch.bfloat16)
+    s1 = torch.randn(n, h, w, 128, device=cuda_dev, generator=g).to(torch.bfloat16)
+    chunks = [(0, 0), (1, 64)] if kc == 64 else [(0, 0), (0, 32), (1, 32)]
+    cin = kc * len(chunks)
+    cout = bn if bn >= 32 else 3
+    wt = torch.randn(cout, cin, 3, 3, device=cuda_dev, generator=g) / (cin * 9) ** 0.5
+    bias = torch.randn(cout, device=cuda_dev, generator=g)
+    wp = K.pack_conv3x3_weights(wt, kc, bn, [i * kc for i in range(len(chunks))])
+    bias_p = torch.zeros(bn, device=cuda_dev)
+    bias_p[:cout] = bias
+    ref = _ref_conv([s0, s1], chunks, kc, wt, bias, act=1)
+    scale = max(1.0, ref.abs().max().item())
+    if cout < 16:  # Cout=3 tail conv (HR_conv1): NCHW fp32 output straight to the caller's tensor
+        out = torch.full((n, cout, h, w), float("nan"), device=cuda_dev)
+        K.ConvCall(n=n, h=h, w=w, srcs=[s0, s1], kc=kc, chunks=chunks, bn=bn, cout=cout, w_packed=wp,
+                   bias=bias_p, act=1, out_nchw=out, variant=variant).launch()
+        assert (out - ref).abs().max().item() <= 2e-3 * scale
+        return
+    out = torch.full((n, h, w, 192), float("nan"), device=cuda_dev, dtype=torch.bfloat16)
+    K.ConvCall(n=n, h=h, w=w, srcs=[s0, s1], kc=kc, chunks=chunks, bn=bn, cout=cout, w_packed=wp,
+               bias=bias_p, act=1, out_bf16=out, ob_c0=64, variant=variant).launch()
+    got = out[..., 64:64 + cout].float().permute(0, 3, 1, 2)
+    assert (got - ref).abs().max().item() <= 1e-2 * scale
+    # concat-free write: only the addressed channel slice is touched
+    assert torch.isnan(out[..., :64].float()).all() and torch.isnan(out[..., 64 + cout:].float()).all()
+
+
+@pytest.mark.parametrize("kc,bn", [(64, 32), (32, 32), (64, 64)])
+def test_conv3x3_fused_epilogue(cuda_dev, kc, bn):
+    """bias + LeakyReLU + s0 + conv1x1 aux + fp32 residual + bf16 RRDB residual, both output twins
+    (block.py:262-268, 291)."""
+    n, h, w = 2, 20, 27
+    g = torch.Generator(device=cuda_dev).manual_seed(99 + kc + bn)
+    s0 = torch.randn(n, h, w, 64, device=cuda_dev, generator=g).to(torch.bfloat16)
+    s1 = torch.randn(n, h, w, 128, device=cuda_dev, generator=g).to(torch.bfloat16)
+    chunks = [(0, 0), (1, 64)] if kc == 64 else [(0, 0), (0, 32), (1, 32)]
+    cin, cout = kc * len(chunks), bn
+    wt = torch.randn(cout, cin, 3, 3, device=cuda_dev, generator=g) / (cin * 9) ** 0.5
+    bias = torch.randn(cout, device=cuda_dev, generator=g)
+    wa = torch.randn(cout, kc, 1, 1, device=cuda_dev, generator=g) / kc ** 0.5
+    wp = K.pack_conv3x3_weights(wt, kc, bn, [i * kc for i in range(len(chunks))])
+    wap = K.pack_conv1x1_weights(wa, kc, bn, [0])
+    r1 = torch.randn(n, h, w, 64, device=cuda_dev, generator=g)
+    r2 = torch.randn(n, h, w, 64, device=cuda_dev, generator=g).to(torch.bfloat16)
+    out_b = torch.zeros((n, h, w, 64), device=cuda_dev, dtype=torch.bfloat16)
+    out_f = torch.zeros((n, h, w, 64), device=cuda_dev)
+    K.ConvCall(n=n, h=h, w=w, srcs=[s0, s1], kc=kc, chunks=chunks, bn=bn, cout=cout, w_packed=wp, bias=bias,
+               act=1, s0=0.5, w_aux=wap, aux_chunks=1, r1=r1, s1=0.25, r2=r2, s2=0.2, out_bf16=out_b,
+               out_f32=out_f).launch()
+    ref = _ref_conv([s0, s1], chunks, kc, wt, bias, act=1)
+    aux = F.conv2d(s0[..., :kc].float().permute(0, 3, 1, 2).contiguous(), wa.to(torch.bfloat16).float())
+    v = 0.5 * ref + aux + 0.25 * r1[..., :cout].permute(0, 3, 1, 2)
+    v = 0.2 * v + r2[..., :cout].float().permute(0, 3, 1, 2)
+    scale = max(1.0, v.abs().max().item())
+    assert (out_f[..., :cout].permute(0, 3, 1, 2) - v).abs().max().item() <= 2e-3 * scale
+    assert (out_b[..., :cout].float().permute(0, 3, 1, 2) - v).abs().max().item() <= 1e-2 * scale
+
+
+def test_conv3x3_rejects_bad_arguments(cuda_dev):
+    s0 = torch.zeros(1, 8, 8, 64, device=cuda_dev, dtype=torch.bfloat16)
+    wp = torch.zeros(9 * 32 * 64 * 2, device=cuda_dev, dtype=torch.uint8)
+    out = torch.zeros(1, 8, 8, 32, device=cuda_dev, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="kc"):
+        K.ConvCall(n=1, h=8, w=8, srcs=[s0], kc=48, chunks=[(0, 0)], bn=32, cout=32, w_packed=wp, out_bf16=out).launch()
+    with pytest.raises(RuntimeError, match="channel range"):
+        K.ConvCall(n=1, h=8, w=8, srcs=[s0], kc=64, chunks=[(0, 32)], bn=32, cout=32, w_packed=wp, out_bf16=out).launch()
+
+
+def test_layout_converters_bit_exact(cuda_dev):
+    x = torch.randn(2, 3, 19, 23, device=cuda_dev)
+    y = K.nchw_f32_to_nhwc_bf16(x, 32)
+    ref = torch.zeros(2, 19, 23, 32, device=cuda_dev, dtype=torch.bfloat16)
+    ref[..., :3] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+    assert torch.equal(y, ref)
+    z = torch.randn(2, 9, 11, 64, device=cuda_dev).to(torch.bfloat16)
+    assert torch.equal(K.upsample2x_nhwc_bf16(z), z.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2))
+    assert torch.equal(K.nhwc_bf16_to_nchw_f32(z, 64), z.float().permute(0, 3, 1, 2).contiguous())
+
+
+# ---------------------------------------------------------------------------------------------------
+# whole generator vs fixtures from the reference
+# ---------------------------------------------------------------------------------------------------
+def _make(cls, sd, nf, nb, dev):
+    net = cls(3, 3, nf, nb, gc=32, upscale=4, norm_type=None, act_type="leakyrelu", mode="CNA", upsample_mode="upconv")
+    net.load_state_dict(sd, strict=True)  # base_model.py:60-63
+    net.eval()
+    for _, p in net.named_parameters():   # test_image/test.py:19-20
+        p.requires_grad = False
+    return net.to(dev)
+
+
+@pytest.mark.parametrize("cls", [E.RRDBNet, E.RRDB_Net])
+def test_rrdbnet_config1_matches_reference_fixture(cuda_dev, golden_dir, cls):
+    g = _golden(golden_dir, "rrdbnet_c1_nb1_nf32.npz")
+    sd = O.synth_state_dict_g(3, 3, 32, 1, seed=21)
+    net = _make(cls, sd, 32, 1, cuda_dev)
+    y = net(torch.from_numpy(g["x"]).to(cuda_dev)).cpu()
+    _net_close(y, torch.from_numpy(g["y"]), "config 1")
+    # test_image/test.py:31-40 plumbing: uint8 BGR -> /255 -> RGB CHW -> model -> clamp -> *255 round
+    img = g["img_u8"] * 1.0 / 255
+    t = torch.from_numpy(np.transpose(img[:, :, [2, 1, 0]], (2, 0, 1))).float().unsqueeze(0).to(cuda_dev)
+    out = net(t).data.squeeze().float().cpu().clamp_(0, 1).numpy()
+    out = (np.transpose(out[[2, 1, 0], :, :], (1, 2, 0)) * 255.0).round().astype("uint8")
+    diff = np.abs(out.astype(int) - g["out_u8"].astype(int))
+    assert diff.max() <= 2 and (diff > 0).mean() < 0.25, (diff.max(), (diff > 0).mean())
+
+
+def test_rrdbnet_nb23_matches_reference_fixture(cuda_dev, golden_dir):
+    g = _golden(golden_dir, "rrdbnet_nb23_nf64.npz")
+    sd = O.synth_state_dict_g(3, 3, 64, 23, seed=31)
+    net = _make(E.RRDBNet, sd, 64, 23, cuda_dev)
+    _net_close(net(torch.from_numpy(g["x24"]).to(cuda_dev)).cpu(), torch.from_numpy(g["y24"]), "nb23 24x24")
+    # ragged: batch 2 of 19x37, no dimension a multiple of the 16x16 CTA tile
+    _net_close(net(torch.from_numpy(g["x_ragged"]).to(cuda_dev)).cpu(), torch.from_numpy(g["y_ragged"]), "nb23 ragged")
+
+
+def test_weight_cache_follows_parameter_updates(cuda_dev):
+    sd_a = O.synth_state_dict_g(3, 3, 32, 1, seed=1)
+    sd_b = O.synth_state_dict_g(3, 3, 32, 1, seed=2)
+    net = _make(E.RRDBNet, sd_a, 32, 1, cuda_dev)
+    x = torch.rand(1, 3, 16, 16)
+    ya = net(x.to(cuda_dev)).cpu()
+    net.load_state_dict(sd_b, strict=True)        # in-place copy_ bumps ._version -> repack
+    yb = net(x.to(cuda_dev)).cpu()
+    _net_close(ya, O.rrdbnet_forward(x, sd_a, 1), "sd_a")
+    _net_close(yb, O.rrdbnet_forward(x, sd_b, 1), "sd_b")
+    with torch.no_grad():
+        for p in net.parameters():                # optimizer-style in-place update
+            p.mul_(0.5)
+    yc = net(x.to(cuda_dev)).cpu()
+    sd_c = {k: v * 0.5 for k, v in sd_b.items()}
+    _net_close(yc, O.rrdbnet_forward(x, sd_c, 1), "sd_c")
+
+
+def test_train_mode_noise_matches_oracle_with_same_draws(cuda_dev):
+    """nESRGAN+ noise (block.py:117-121): the kernel draws N(0,1) from Philox(seed, rdb_index<<36 + e/4);
+    esrp_philox_normal_host regenerates the identical draws so the oracle can be fed the same tensor."""
+    lib = _lib.load()
+    nb, nf, n, h, w = 2, 32, 2, 12, 20
+    sd = O.synth_state_dict_g(3, 3, nf, nb, seed=77)
+    net = _make(E.RRDBNet, sd, nf, nb, cuda_dev)
+    net.train()
+    x = torch.rand(n, 3, h, w)
+    torch.manual_seed(1234)
+    with torch.no_grad():
+        y = net(x.to(cuda_dev)).cpu()
+        seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + net._step) & 0xFFFFFFFFFFFFFFFF
+        noises = []
+        for i in range(nb):
+            row = []
+            for r in range(3):
+                buf = np.empty(n * h * w * nf, dtype=np.float32)
+                assert lib.esrp_philox_normal_host(seed, (i * 3 + r) << 36, buf.size, buf.ctypes.data) == 0
+                row.append(torch.from_numpy(buf).reshape(n, h, w, nf).permute(0, 3, 1, 2).contiguous())
+            noises.append(row)
+        ref = O.rrdbnet_forward(x, sd, nb, training=True, noises=noises)
+        ref_eval = O.rrdbnet_forward(x, sd, nb)
+    _net_close(y, ref, "train-mode noise")
+    assert (ref - ref_eval).abs().max() > 10 * (y - ref).abs().max(), "noise must matter more than the tolerance"
+    # draws are N(0,1)
+    z = torch.cat([t.flatten() for row in noises for t in row])
+    assert abs(z.mean().item()) < 0.02 and abs(z.std().item() - 1.0) < 0.02
+    # eval() switches it off; a new call draws new noise; the same seed+step reproduces
+    with torch.no_grad():
+        y2 = net(x.to(cuda_dev)).cpu()
+    assert not torch.equal(y, y2)
+    net.eval()
+    with torch.no_grad():
+        _net_close(net(x.to(cuda_dev)).cpu(), ref_eval, "eval after train")
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json config 2 size: 16 tiles of 128x128, nb=23 nf=64 — size-independent properties
+# ---------------------------------------------------------------------------------------------------
+def test_config2_full_size_properties(cuda_dev):
+    sd = O.synth_state_dict_g(3, 3, 64, 23, seed=31)
+    net = _make(E.RRDBNet, sd, 64, 23, cuda_dev)
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(16, 3, 128, 128, generator=g)
+    xd = x.to(cuda_dev)
+    y = net(xd)
+    assert y.shape == (16, 3, 512, 512) and torch.isfinite(y).all()
+    # determinism: the kernels have no atomics / split-K on the forward path
+    assert torch.equal(y, net(xd))
+    # tiles are independent units: a tile's result does not depend on its batch mates
+    perm = torch.arange(15, -1, -1)
+    assert torch.equal(net(xd[perm])[perm], y)
+    y1 = net(xd[3:4])
+    assert torch.equal(y1[0], y[3])
+    # one tile against the fp32 oracle at full tile size
+    ref = O.rrdbnet_forward(x[3:4], sd, 23)
+    _net_close(y1.cpu(), ref, "config 2 tile 3")
