@@ -10,8 +10,18 @@ import ctypes as C
 import os
 
 ESRP_MAX_CHUNKS = 8
-VARIANT_ALIGNED = 1
-VARIANT_MT1 = 2
+LAYOUT_TILE = 0   # kx-stacked RM x CW tiles (conv3x3_tc.cuh): any width, narrow images
+LAYOUT_ROW = 1    # ky-stacked row streaming (conv3x3_row.cuh): images wider than ~64 px, bn <= 32
+
+
+def variant_mt(mt: int) -> int:
+    """esrp_conv3x3_t.variant bits forcing `mt` accumulator slots per CTA tile (ESRP_VARIANT_MT)."""
+    return mt & 15
+
+
+def variant_cwlog2(l: int) -> int:
+    """variant bits forcing the M-tile width 2**l pixels (ESRP_VARIANT_CWLOG2)."""
+    return (l & 15) << 4
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libesrp.so")
@@ -32,7 +42,7 @@ class Conv3x3Desc(C.Structure):
         ("bn", C.c_int32),
         ("cout", C.c_int32),
         ("w_packed", C.c_void_p),
-        ("w_aux", C.c_void_p),
+        ("w_layout", C.c_int32),
         ("bias", C.c_void_p),
         ("act", C.c_int32),
         ("s0", C.c_float),
@@ -43,6 +53,7 @@ class Conv3x3Desc(C.Structure):
         ("r2_is_f32", C.c_int32), ("r2_ctotal", C.c_int32), ("r2_c0", C.c_int32),
         ("s2", C.c_float),
         ("noise", C.c_int32),
+        ("noise_ctotal", C.c_int32), ("noise_c0", C.c_int32),
         ("sigma", C.c_float),
         ("seed", C.c_uint64), ("offset", C.c_uint64),
         ("out_bf16", C.c_void_p),
@@ -51,6 +62,7 @@ class Conv3x3Desc(C.Structure):
         ("of_ctotal", C.c_int32), ("of_c0", C.c_int32),
         ("out_nchw", C.c_void_p),
         ("variant", C.c_int32),
+        ("trace", C.c_void_p),
     ]
 
 
@@ -62,12 +74,10 @@ SYMBOLS = {
     "esrp_sizeof_conv3x3": (C.c_int32, []),
     "esrp_philox_normal_host": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p]),
     "esrp_conv3x3_nhwc": (C.c_int, [C.POINTER(Conv3x3Desc), C.c_void_p]),
-    "esrp_packed_conv3x3_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
-    "esrp_packed_conv1x1_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
-    "esrp_pack_conv3x3_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                            C.c_int32, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]),
-    "esrp_pack_conv1x1_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                            C.c_int32, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]),
+    "esrp_packed_conv3x3_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "esrp_pack_conv3x3_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_void_p,
+                                            C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "esrp_nchw_f32_to_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                              C.c_int32, C.c_int32, C.c_void_p]),
     "esrp_nhwc_bf16_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,

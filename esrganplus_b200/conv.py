@@ -21,31 +21,31 @@ def _i32_array(vals: Sequence[int]):
     return arr
 
 
-def pack_conv3x3_weights(w_oihw: torch.Tensor, kc: int, bn: int, chunk_lc0: Sequence[int]) -> torch.Tensor:
-    """OIHW fp32 (device) -> pre-swizzled bf16 UMMA B tiles [chunk][tap][bn][kc] (opaque bytes)."""
+def pack_conv3x3_weights(w_oihw: torch.Tensor, kc: int, bn: int, chunk_lc0: Sequence[int],
+                         w_aux: Optional[torch.Tensor] = None, aux_chunks: int = 0, row0: int = 0,
+                         rows: Optional[int] = None, transpose: bool = False,
+                         layout: int = _lib.LAYOUT_TILE) -> torch.Tensor:
+    """[O, I, 3, 3] fp32 (device) -> pre-swizzled bf16 UMMA B tiles [chunk][ky][kx*bn + r (, conv1x1)][kc]
+    (opaque bytes).  `w_aux` is the bias-free 1x1 conv [O, I_aux(,1,1)] fused on the first `aux_chunks`
+    chunks; `transpose` packs the data-gradient operator (see include/esrp.h)."""
     lib = _lib.load()
     assert w_oihw.is_cuda and w_oihw.dtype == torch.float32 and w_oihw.dim() == 4
     w = w_oihw.contiguous()
-    cout, cin, kh, kw = w.shape
+    w_o, w_i, kh, kw = w.shape
     assert kh == 3 and kw == 3
-    nbytes = lib.esrp_packed_conv3x3_bytes(len(chunk_lc0), kc, bn)
+    if rows is None:
+        rows = min(bn, (w_i if transpose else w_o) - row0)
+    aux_ptr, aux_cin = None, 0
+    if w_aux is not None:
+        assert w_aux.is_cuda and w_aux.dtype == torch.float32
+        w_aux = w_aux.reshape(w_aux.shape[0], w_aux.shape[1]).contiguous()
+        aux_ptr, aux_cin = w_aux.data_ptr(), w_aux.shape[1]
+    nbytes = lib.esrp_packed_conv3x3_bytes(len(chunk_lc0), kc, bn, int(aux_chunks > 0))
     out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
-    _lib.check(lib.esrp_pack_conv3x3_weights(w.data_ptr(), cout, cin, kc, bn, len(chunk_lc0),
-                                             _i32_array(chunk_lc0), out.data_ptr(), _stream_ptr()),
+    _lib.check(lib.esrp_pack_conv3x3_weights(w.data_ptr(), w_o, w_i, int(transpose), layout, row0, rows, kc, bn,
+                                             len(chunk_lc0), _i32_array(chunk_lc0), aux_ptr, aux_cin, aux_chunks,
+                                             out.data_ptr(), _stream_ptr()),
                "esrp_pack_conv3x3_weights")
-    return out
-
-
-def pack_conv1x1_weights(w: torch.Tensor, kc: int, bn: int, chunk_lc0: Sequence[int]) -> torch.Tensor:
-    lib = _lib.load()
-    assert w.is_cuda and w.dtype == torch.float32
-    w2 = w.reshape(w.shape[0], w.shape[1]).contiguous()
-    cout, cin = w2.shape
-    nbytes = lib.esrp_packed_conv1x1_bytes(len(chunk_lc0), kc, bn)
-    out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
-    _lib.check(lib.esrp_pack_conv1x1_weights(w2.data_ptr(), cout, cin, kc, bn, len(chunk_lc0),
-                                             _i32_array(chunk_lc0), out.data_ptr(), _stream_ptr()),
-               "esrp_pack_conv1x1_weights")
     return out
 
 
@@ -62,9 +62,9 @@ class ConvCall:
     bn: int
     cout: int
     w_packed: torch.Tensor
+    w_layout: int = _lib.LAYOUT_TILE         # must match the layout w_packed was packed with
     bias: Optional[torch.Tensor] = None      # fp32 [bn]
-    w_aux: Optional[torch.Tensor] = None
-    aux_chunks: int = 0
+    aux_chunks: int = 0                      # leading chunks feeding the fused conv1x1 rows of w_packed
     act: int = 0
     s0: float = 1.0
     r1: Optional[torch.Tensor] = None
@@ -74,6 +74,8 @@ class ConvCall:
     r2_c0: int = 0
     s2: float = 1.0
     noise: int = 0
+    noise_ctotal: int = 0
+    noise_c0: int = 0
     sigma: float = 0.1
     seed: int = 0
     offset: int = 0
@@ -83,6 +85,7 @@ class ConvCall:
     of_c0: int = 0
     out_nchw: Optional[torch.Tensor] = None
     variant: int = 0
+    trace: Optional[torch.Tensor] = None     # int64 [3*1024] device tensor (CTA 0 timeline)
     _keep: list = field(default_factory=list, repr=False)
 
     def desc(self) -> Conv3x3Desc:
@@ -101,7 +104,7 @@ class ConvCall:
         d.aux_chunks = self.aux_chunks
         d.bn, d.cout = self.bn, self.cout
         d.w_packed = self.w_packed.data_ptr()
-        d.w_aux = self.w_aux.data_ptr() if self.w_aux is not None else None
+        d.w_layout = self.w_layout
         d.bias = self.bias.data_ptr() if self.bias is not None else None
         d.act, d.s0 = self.act, self.s0
         for name in ("r1", "r2"):
@@ -114,6 +117,7 @@ class ConvCall:
                 setattr(d, name + "_c0", getattr(self, name + "_c0"))
         d.s1, d.s2 = self.s1, self.s2
         d.noise, d.sigma, d.seed, d.offset = self.noise, self.sigma, self.seed, self.offset
+        d.noise_ctotal, d.noise_c0 = (self.noise_ctotal or self.cout), self.noise_c0
         if self.out_bf16 is not None:
             assert self.out_bf16.dtype == torch.bfloat16 and self.out_bf16.is_contiguous()
             d.out_bf16, d.ob_ctotal, d.ob_c0 = self.out_bf16.data_ptr(), self.out_bf16.shape[3], self.ob_c0
@@ -124,6 +128,7 @@ class ConvCall:
             assert self.out_nchw.dtype == torch.float32 and self.out_nchw.is_contiguous()
             d.out_nchw = self.out_nchw.data_ptr()
         d.variant = self.variant
+        d.trace = self.trace.data_ptr() if self.trace is not None else None
         return d
 
     def launch(self) -> None:

@@ -6,18 +6,25 @@
 
 #include "../../include/esrp.h"
 
+#define ESRP_MAX_MT 5  // M-tile accumulator slots per CTA (TMEM: mt * nt <= 512 columns)
+
 namespace esrp {
 
 struct ConvKParams {
   int n, h, w;
-  int tiles_x, tiles_y, num_tiles;
+  // tiling (see conv3x3_tc.cuh): M-tile = rm rows x cw columns, CTA tile = up to mt M-tiles
+  int cw, cw_log2, rm, mt;
+  int x_tiles, x_step;          // column blocks per image and their source-column advance
+  int units_per_col;            // ceil(h / rm)
+  long long units_total;        // n * x_tiles * units_per_col
+  int nt;                       // TMEM columns per accumulator: 3*BN (+BN with conv1x1)
+  int a_box_bytes, a_stage_bytes;
   int num_chunks;
   int chunk_src[ESRP_MAX_CHUNKS];
   int chunk_c0[ESRP_MAX_CHUNKS];
   int aux_chunks;
   int cout;
   const uint8_t* w_packed;
-  const uint8_t* w_aux;
   const float* bias;
   int w_resident;
   int stages;
@@ -30,7 +37,7 @@ struct ConvKParams {
   const void* r2;
   int r2_is_f32, r2_ctotal, r2_c0;
   float s2;
-  int noise;
+  int noise, noise_ctotal, noise_c0;
   float sigma;
   unsigned long long seed, offset;
   __nv_bfloat16* out_bf16;
@@ -38,6 +45,7 @@ struct ConvKParams {
   float* out_f32;
   int of_ctotal, of_c0;
   float* out_nchw;
+  long long* trace;  // optional [3][1024] clock64 timeline of CTA 0 (see trace_ev)
 };
 
 }  // namespace esrp

@@ -10,7 +10,8 @@
 #include <mutex>
 
 #include "../../include/esrp.h"
-#include "conv3x3_tc.cuh"
+#include "conv3x3_row.cuh"
+#include "conv3x3_tc.cuh"  // kSmemFixed, kMaxStages, kernel template
 #include "esrp_host.h"
 
 namespace esrp {
@@ -86,19 +87,9 @@ int sm_count() {
   return g_sm_count;
 }
 
-template <int KC, int BN, int MT, bool HALO>
-static int plan_conv_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
-  using G = ConvGeom<KC, MT, HALO>;
-  constexpr int RB = G::RB;
-  constexpr int W_CHUNK_BYTES = 9 * BN * RB;
-  constexpr int W_AUX_BYTES = BN * RB;
-
-  ConvKParams& p = out->params;
-  memset(&p, 0, sizeof(p));
-  p.n = d.n; p.h = d.h; p.w = d.w;
-  p.tiles_x = (d.w + G::TW - 1) / G::TW;
-  p.tiles_y = (d.h + kTileH - 1) / kTileH;
-  p.num_tiles = p.tiles_x * p.tiles_y * d.n;
+// descriptor fields that map 1:1 onto kernel parameters (both kernels)
+static void copy_common(const esrp_conv3x3_t& d, ConvKParams* pp) {
+  ConvKParams& p = *pp;
   p.num_chunks = d.num_chunks;
   for (int i = 0; i < d.num_chunks; ++i) {
     p.chunk_src[i] = d.chunk_src[i];
@@ -107,57 +98,174 @@ static int plan_conv_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
   p.aux_chunks = d.aux_chunks;
   p.cout = d.cout;
   p.w_packed = static_cast<const uint8_t*>(d.w_packed);
-  p.w_aux = static_cast<const uint8_t*>(d.w_aux);
   p.bias = d.bias;
   p.act = d.act; p.s0 = d.s0;
   p.r1 = d.r1; p.r1_is_f32 = d.r1_is_f32; p.r1_ctotal = d.r1_ctotal; p.r1_c0 = d.r1_c0; p.s1 = d.s1;
   p.r2 = d.r2; p.r2_is_f32 = d.r2_is_f32; p.r2_ctotal = d.r2_ctotal; p.r2_c0 = d.r2_c0; p.s2 = d.s2;
-  p.noise = d.noise; p.sigma = d.sigma; p.seed = d.seed; p.offset = d.offset;
+  p.noise = d.noise; p.noise_ctotal = d.noise_ctotal; p.noise_c0 = d.noise_c0;
+  p.sigma = d.sigma; p.seed = d.seed; p.offset = d.offset;
   p.out_bf16 = static_cast<__nv_bfloat16*>(d.out_bf16); p.ob_ctotal = d.ob_ctotal; p.ob_c0 = d.ob_c0;
   p.out_f32 = static_cast<float*>(d.out_f32); p.of_ctotal = d.of_ctotal; p.of_c0 = d.of_c0;
   p.out_nchw = d.out_nchw;
+  p.trace = static_cast<long long*>(d.trace);
+}
 
+// ky-stacked row-streaming kernel (conv3x3_row.cuh)
+template <int KC, int BN>
+static int plan_row_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
+  constexpr int RB = KC * 2;
+  ConvKParams& p = out->params;
+  memset(&p, 0, sizeof(p));
+  p.n = d.n; p.h = d.h; p.w = d.w;
   const bool has_aux = d.aux_chunks > 0;
-  const int bnt = has_aux ? 2 * BN : BN;
+  const int nb_rows = (has_aux ? 4 : 3) * BN;
+  const int w_chunk_bytes = 3 * nb_rows * RB;
+  const int w_all = d.num_chunks * w_chunk_bytes;
+  p.nt = nb_rows;
+  int ns = 512 / p.nt;
+  if (ns > kMaxSlots) ns = kMaxSlots;
+  const int force = d.variant & 15;
+  if (force) ns = force;
+  if (ns < 3 || ns * p.nt > 512 || ns > kMaxSlots) return set_error("conv3x3(row): %d TMEM slots of %d columns unsupported", ns, p.nt);
+  p.mt = ns;
+  p.cw = kRowTile; p.cw_log2 = 7; p.rm = 1;
+  p.x_tiles = (d.w + kRowTile - 1) / kRowTile;
+  p.x_step = kRowTile;
+  p.units_per_col = d.h;
+  p.units_total = static_cast<long long>(d.n) * p.x_tiles * d.h;
+  if (p.units_total > 0x7fffffffLL) return set_error("conv3x3: problem too large (%lld rows)", p.units_total);
+  p.a_box_bytes = (kRowTile + 2) * RB;
+  p.a_stage_bytes = (p.a_box_bytes + 1023) / 1024 * 1024;
+  const int avail = kMaxSmem - kSmemFixed - 1024;
+  const int s_res = w_all <= avail ? (avail - w_all) / p.a_stage_bytes : 0;
+  const int s_str = avail / (p.a_stage_bytes + w_chunk_bytes);
+  if (s_res >= 3) { p.w_resident = 1; p.stages = s_res; }
+  else if (s_str >= 2) { p.w_resident = 0; p.stages = s_str; }
+  else if (s_res >= 1) { p.w_resident = 1; p.stages = s_res; }
+  else return set_error("conv3x3(row): weights do not fit in shared memory (KC=%d BN=%d chunks=%d)", KC, BN, d.num_chunks);
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
   uint32_t cols = 32;
-  while (cols < static_cast<uint32_t>(2 * MT * bnt)) cols <<= 1;
-  if (cols > 512) return set_error("conv3x3: TMEM budget exceeded (MT=%d BN=%d aux=%d)", MT, BN, has_aux);
+  while (cols < static_cast<uint32_t>(p.mt * p.nt)) cols <<= 1;
   p.tmem_cols = cols;
-
-  // shared memory plan: 1 KB align slack + 1 KB barriers + [resident weights] + stages
-  const int w_all = d.num_chunks * W_CHUNK_BYTES + d.aux_chunks * W_AUX_BYTES;
-  const int fixed = 2048;
-  int stage_res = G::A_BYTES;
-  int stage_str = G::A_BYTES + W_CHUNK_BYTES + (has_aux ? W_AUX_BYTES : 0);
-  int s_res = (kMaxSmem - fixed - w_all) / stage_res;
-  int s_str = (kMaxSmem - fixed) / stage_str;
-  if (s_res >= 2 || (s_res >= 1 && s_str < 1)) {
-    p.w_resident = 1;
-    p.stages = s_res > 8 ? 8 : s_res;
-  } else {
-    p.w_resident = 0;
-    p.stages = s_str > 8 ? 8 : s_str;
-  }
-  if (p.stages < 1) return set_error("conv3x3: tile does not fit in shared memory (KC=%d BN=%d MT=%d)", KC, BN, MT);
-  out->smem = fixed + (p.w_resident ? w_all : 0) + p.stages * (p.w_resident ? stage_res : stage_str);
-
-  if (make_nhwc_tmap(&out->tm0, d.src[0], d.n, d.h, d.w, d.src_ctotal[0], KC, G::HW, G::HH)) return 1;
+  out->smem = kSmemFixed + 1024 + (p.w_resident ? w_all : 0) +
+              p.stages * (p.a_stage_bytes + (p.w_resident ? 0 : w_chunk_bytes));
+  copy_common(d, &p);
+  if (make_nhwc_tmap(&out->tm0, d.src[0], d.n, d.h, d.w, d.src_ctotal[0], KC, kRowTile + 2, 1)) return 1;
   if (d.src[1]) {
-    if (make_nhwc_tmap(&out->tm1, d.src[1], d.n, d.h, d.w, d.src_ctotal[1], KC, G::HW, G::HH)) return 1;
+    if (make_nhwc_tmap(&out->tm1, d.src[1], d.n, d.h, d.w, d.src_ctotal[1], KC, kRowTile + 2, 1)) return 1;
+  } else {
+    out->tm1 = out->tm0;
+  }
+  auto kern = conv3x3_row_kernel<KC, BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ESRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    attr_set = true;
+  }
+  out->kernel = reinterpret_cast<const void*>(kern);
+  out->threads = kRowThreads;
+  const int sms = sm_count();
+  if (sms <= 0) return set_error("conv3x3: no CUDA device");
+  out->grid = p.units_total < sms ? static_cast<int>(p.units_total) : sms;
+  return 0;
+}
+
+template <int KC, int BN>
+static int plan_conv_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
+  constexpr int RB = KC * 2;
+  ConvKParams& p = out->params;
+  memset(&p, 0, sizeof(p));
+  p.n = d.n; p.h = d.h; p.w = d.w;
+  const bool has_aux = d.aux_chunks > 0;
+  const int nb_rows = (has_aux ? 4 : 3) * BN;
+  const int w_chunk_bytes = 3 * nb_rows * RB;
+  const int w_all = d.num_chunks * w_chunk_bytes;
+  p.nt = nb_rows;
+
+  // M-tile width: the smallest of 16/32/64/128 columns covering the image, else 128 with x-halo blocks
+  int cwl = 4;
+  while (cwl < 7 && (1 << cwl) < d.w) ++cwl;
+  const int force_cwl = (d.variant >> 4) & 15;
+  if (force_cwl) {
+    if (force_cwl < 4 || force_cwl > 7) return set_error("conv3x3: variant forces cw_log2=%d (4..7)", force_cwl);
+    cwl = force_cwl;
+  }
+  p.cw_log2 = cwl;
+  p.cw = 1 << cwl;
+  p.rm = 128 >> cwl;
+  if (d.w <= p.cw) {
+    p.x_tiles = 1;
+    p.x_step = p.cw;
+  } else {
+    p.x_step = p.cw - 2;
+    p.x_tiles = (d.w - 1 + p.x_step - 1) / p.x_step;
+  }
+  p.units_per_col = (d.h + p.rm - 1) / p.rm;
+  p.units_total = static_cast<long long>(d.n) * p.x_tiles * p.units_per_col;
+  if (p.units_total > 0x7fffffffLL) return set_error("conv3x3: problem too large (%lld M-tiles)", p.units_total);
+
+  // accumulator slots per CTA tile: TMEM (mt * nt <= 512) and shared memory (>= 2 stages) permitting
+  const int sms = sm_count();
+  if (sms <= 0) return set_error("conv3x3: no CUDA device");
+  const long long per_cta = (p.units_total + sms - 1) / sms;
+  int mt = 512 / p.nt;
+  if (mt > ESRP_MAX_MT) mt = ESRP_MAX_MT;
+  if (mt > per_cta) mt = static_cast<int>(per_cta);
+  if (mt > p.units_per_col) mt = p.units_per_col;
+  const int force_mt = d.variant & 15;
+  if (force_mt) {
+    if (force_mt > ESRP_MAX_MT || force_mt * p.nt > 512) return set_error("conv3x3: variant forces mt=%d (nt=%d)", force_mt, p.nt);
+    mt = force_mt;
+  }
+  const int avail = kMaxSmem - kSmemFixed - 1024;  // 1 KB alignment slack
+  auto a_stage = [&](int m) { return ((m * p.rm + 2) * p.cw * RB + 1023) / 1024 * 1024; };
+  // largest tile with resident weights and >= 2 stages; else stream the weights with the chunks
+  int best_mt = 0, best_res = 0, best_s = 0;
+  for (int pass = 0; pass < 2 && !best_mt; ++pass) {
+    for (int m = mt; m >= 1; --m) {
+      const int s_res = w_all <= avail ? (avail - w_all) / a_stage(m) : 0;
+      const int s_str = avail / (a_stage(m) + w_chunk_bytes);
+      if (pass == 0 && s_res >= 2) { best_mt = m; best_res = 1; best_s = s_res; break; }
+      if (pass == 1 && s_str >= 2) { best_mt = m; best_res = 0; best_s = s_str; break; }
+      if (force_mt) break;
+    }
+  }
+  if (!best_mt) {
+    const int s_res = (avail - w_all) / a_stage(mt), s_str = avail / (a_stage(mt) + w_chunk_bytes);
+    if (w_all <= avail && s_res >= 1) { best_mt = mt; best_res = 1; best_s = s_res; }
+    else if (s_str >= 1) { best_mt = mt; best_res = 0; best_s = s_str; }
+    else return set_error("conv3x3: tile does not fit in shared memory (KC=%d BN=%d chunks=%d)", KC, BN, d.num_chunks);
+  }
+  p.mt = best_mt;
+  p.w_resident = best_res;
+  p.stages = best_s > kMaxStages ? kMaxStages : best_s;
+  p.a_box_bytes = (p.mt * p.rm + 2) * p.cw * RB;
+  p.a_stage_bytes = a_stage(p.mt);
+  uint32_t cols = 32;
+  while (cols < static_cast<uint32_t>(p.mt * p.nt)) cols <<= 1;
+  p.tmem_cols = cols;
+  out->smem = kSmemFixed + 1024 + (p.w_resident ? w_all : 0) +
+              p.stages * (p.a_stage_bytes + (p.w_resident ? 0 : w_chunk_bytes));
+
+  copy_common(d, &p);
+
+  const int box_rows = p.mt * p.rm + 2;
+  if (make_nhwc_tmap(&out->tm0, d.src[0], d.n, d.h, d.w, d.src_ctotal[0], KC, p.cw, box_rows)) return 1;
+  if (d.src[1]) {
+    if (make_nhwc_tmap(&out->tm1, d.src[1], d.n, d.h, d.w, d.src_ctotal[1], KC, p.cw, box_rows)) return 1;
   } else {
     out->tm1 = out->tm0;
   }
 
-  auto kern = conv3x3_tc_kernel<KC, BN, MT, HALO>;
+  auto kern = conv3x3_tc_kernel<KC, BN>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
     ESRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     attr_set = true;
   }
   out->kernel = reinterpret_cast<const void*>(kern);
-  int sms = sm_count();
-  if (sms <= 0) return set_error("conv3x3: no CUDA device");
-  out->grid = p.num_tiles < sms ? p.num_tiles : sms;
+  out->threads = kConvThreads;
+  out->grid = p.units_total < sms ? static_cast<int>(p.units_total) : sms;
   return 0;
 }
 
@@ -165,23 +273,14 @@ int run_conv(const ConvLaunch& L, cudaStream_t stream) {
   if (L.grid < 1) return 0;
   void* args[3] = {const_cast<CUtensorMap*>(&L.tm0), const_cast<CUtensorMap*>(&L.tm1),
                    const_cast<ConvKParams*>(&L.params)};
-  ESRP_CUDA_OK(cudaLaunchKernel(L.kernel, dim3(L.grid), dim3(kConvThreads), args, L.smem, stream));
+  ESRP_CUDA_OK(cudaLaunchKernel(L.kernel, dim3(L.grid), dim3(L.threads), args, L.smem, stream));
   return 0;
-}
-
-template <int KC, int BN>
-static int dispatch_variant(const esrp_conv3x3_t& d, ConvLaunch* out) {
-  const bool aligned = d.variant & ESRP_VARIANT_ALIGNED;
-  const bool mt1 = d.variant & ESRP_VARIANT_MT1;
-  if (aligned) return mt1 ? plan_conv_t<KC, BN, 1, false>(d, out) : plan_conv_t<KC, BN, 2, false>(d, out);
-  return mt1 ? plan_conv_t<KC, BN, 1, true>(d, out) : plan_conv_t<KC, BN, 2, true>(d, out);
 }
 
 int plan_conv(const esrp_conv3x3_t& d, ConvLaunch* out) {
   if (d.n < 1 || d.h < 1 || d.w < 1) return set_error("conv3x3: bad shape n=%d h=%d w=%d", d.n, d.h, d.w);
   if (d.num_chunks < 1 || d.num_chunks > ESRP_MAX_CHUNKS) return set_error("conv3x3: num_chunks=%d out of range", d.num_chunks);
   if (d.aux_chunks < 0 || d.aux_chunks > d.num_chunks) return set_error("conv3x3: aux_chunks=%d out of range", d.aux_chunks);
-  if (d.aux_chunks > 0 && !d.w_aux) return set_error("conv3x3: aux_chunks without w_aux");
   if (!d.src[0] || !d.w_packed) return set_error("conv3x3: null src/weights");
   if (d.cout < 1 || d.cout > d.bn) return set_error("conv3x3: cout=%d vs bn=%d", d.cout, d.bn);
   for (int i = 0; i < d.num_chunks; ++i) {
@@ -197,25 +296,34 @@ int plan_conv(const esrp_conv3x3_t& d, ConvLaunch* out) {
   if (d.out_f32 && ((d.of_ctotal % 4) || (d.of_c0 % 4))) return set_error("conv3x3: out_f32 channel alignment");
   if (d.r1 && ((d.r1_ctotal % 8) || (d.r1_c0 % 8))) return set_error("conv3x3: r1 channel alignment");
   if (d.r2 && ((d.r2_ctotal % 8) || (d.r2_c0 % 8))) return set_error("conv3x3: r2 channel alignment");
-  if ((d.out_bf16 || d.out_f32) && (d.cout % 16)) return set_error("conv3x3: NHWC outputs need cout %% 16 == 0");
+  if ((d.out_bf16 || d.out_f32 || d.r1 || d.r2) && (d.cout % 16)) return set_error("conv3x3: NHWC outputs/residuals need cout %% 16 == 0");
+  if (d.noise && ((d.noise_ctotal % 4) || (d.noise_c0 % 4) || d.noise_ctotal < d.cout)) return set_error("conv3x3: noise_ctotal/noise_c0 must be multiples of 4 and cover cout");
+  if (d.w_layout == ESRP_LAYOUT_ROW) {
+    if (d.kc == 64 && d.bn == 16) return plan_row_t<64, 16>(d, out);
+    if (d.kc == 64 && d.bn == 32) return plan_row_t<64, 32>(d, out);
+    if (d.kc == 32 && d.bn == 16) return plan_row_t<32, 16>(d, out);
+    if (d.kc == 32 && d.bn == 32) return plan_row_t<32, 32>(d, out);
+    return set_error("conv3x3(row): unsupported kc=%d bn=%d (kc in {32,64}, bn in {16,32})", d.kc, d.bn);
+  }
+  if (d.w_layout != ESRP_LAYOUT_TILE) return set_error("conv3x3: unknown w_layout=%d", d.w_layout);
   if (d.kc == 64) {
     switch (d.bn) {
-      case 16: return dispatch_variant<64, 16>(d, out);
-      case 32: return dispatch_variant<64, 32>(d, out);
-      case 64: return dispatch_variant<64, 64>(d, out);
+      case 16: return plan_conv_t<64, 16>(d, out);
+      case 32: return plan_conv_t<64, 32>(d, out);
+      case 64: return plan_conv_t<64, 64>(d, out);
     }
   } else if (d.kc == 32) {
     switch (d.bn) {
-      case 16: return dispatch_variant<32, 16>(d, out);
-      case 32: return dispatch_variant<32, 32>(d, out);
-      case 64: return dispatch_variant<32, 64>(d, out);
+      case 16: return plan_conv_t<32, 16>(d, out);
+      case 32: return plan_conv_t<32, 32>(d, out);
+      case 64: return plan_conv_t<32, 64>(d, out);
     }
   }
   return set_error("conv3x3: unsupported kc=%d bn=%d (kc in {32,64}, bn in {16,32,64})", d.kc, d.bn);
 }
 
 // ------------------------------------------------------------------------------------------------
-// weight repack: OIHW fp32 -> [chunk][tap][bn][kc] bf16, rows pre-swizzled for UMMA/TMA
+// weight repack: [w_o, w_i, 3, 3] fp32 -> [chunk][ky][row][kc] bf16, rows pre-swizzled for UMMA/TMA
 // ------------------------------------------------------------------------------------------------
 struct ChunkTable {
   int lc0[ESRP_MAX_CHUNKS];
@@ -228,38 +336,36 @@ __device__ __forceinline__ int swizzled_elem(int row, int k, int kc) {
   return row * kc + (((chunk16 ^ x) << 3) | (k & 7));
 }
 
-__global__ void pack_conv_weights_kernel(const float* __restrict__ w, int cout, int cin, int taps,
-                                         int kc, int bn, int num_chunks, ChunkTable tab,
+__global__ void pack_conv_weights_kernel(const float* __restrict__ w, int w_o, int w_i, int transpose, int layout, int row0,
+                                         int rows, int kc, int bn, int num_chunks, ChunkTable tab,
+                                         const float* __restrict__ w_aux, int aux_cin, int aux_chunks,
                                          __nv_bfloat16* __restrict__ out) {
-  const int total = num_chunks * taps * bn * kc;
+  const int nb_rows = (aux_chunks > 0 ? 4 : 3) * bn;
+  const int total = num_chunks * 3 * nb_rows * kc;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int k = i % kc;
-    const int row = (i / kc) % bn;
-    const int tap = (i / (kc * bn)) % taps;
-    const int chunk = i / (kc * bn * taps);
+    const int row = (i / kc) % nb_rows;
+    const int outer = (i / (kc * nb_rows)) % 3;  // MMA index within a K-slice: ky (TILE) / kx (ROW)
+    const int chunk = i / (kc * nb_rows * 3);
+    const int blk = row / bn;        // 0..2: tap stacked along N: kx (TILE) / ky (ROW); 3: conv1x1 rows
+    const int r = row - blk * bn;    // logical output channel within the packed slice
     const int ci = tab.lc0[chunk] + k;
+    const int ky = layout == ESRP_LAYOUT_ROW ? blk : outer;
     float v = 0.f;
-    if (row < cout && ci < cin) v = w[(static_cast<size_t>(row) * cin + ci) * taps + tap];
-    out[static_cast<size_t>(chunk * taps + tap) * bn * kc + swizzled_elem(row, k, kc)] = __float2bfloat16_rn(v);
+    if (r < rows) {
+      if (blk < 3) {
+        const int kx = layout == ESRP_LAYOUT_ROW ? outer : blk;
+        if (!transpose) {
+          if (row0 + r < w_o && ci < w_i) v = w[((static_cast<size_t>(row0 + r) * w_i + ci) * 3 + ky) * 3 + kx];
+        } else {
+          if (ci < w_o && row0 + r < w_i) v = w[((static_cast<size_t>(ci) * w_i + row0 + r) * 3 + (2 - ky)) * 3 + (2 - kx)];
+        }
+      } else if (outer == 1 && chunk < aux_chunks && w_aux != nullptr) {
+        if (row0 + r < w_o && ci < aux_cin) v = w_aux[static_cast<size_t>(row0 + r) * aux_cin + ci];
+      }
+    }
+    out[static_cast<size_t>(chunk * 3 + outer) * nb_rows * kc + swizzled_elem(row, k, kc)] = __float2bfloat16_rn(v);
   }
-}
-
-static int pack_weights(const float* w, int cout, int cin, int taps, int kc, int bn, int num_chunks,
-                        const int32_t* lc0, void* out, cudaStream_t stream) {
-  if (!w || !out || !lc0) return set_error("pack_weights: null pointer");
-  if (kc != 32 && kc != 64) return set_error("pack_weights: kc must be 32 or 64");
-  if (bn % 16 || bn < 16 || bn > 256 || cout > bn) return set_error("pack_weights: bad bn=%d cout=%d", bn, cout);
-  if (num_chunks < 1 || num_chunks > ESRP_MAX_CHUNKS) return set_error("pack_weights: num_chunks=%d", num_chunks);
-  ChunkTable tab;
-  for (int i = 0; i < ESRP_MAX_CHUNKS; ++i) tab.lc0[i] = i < num_chunks ? lc0[i] : 0;
-  const int total = num_chunks * taps * bn * kc;
-  const int threads = 256;
-  int blocks = (total + threads - 1) / threads;
-  if (blocks > 1024) blocks = 1024;
-  pack_conv_weights_kernel<<<blocks, threads, 0, stream>>>(w, cout, cin, taps, kc, bn, num_chunks, tab,
-                                                           static_cast<__nv_bfloat16*>(out));
-  ESRP_CUDA_OK(cudaGetLastError());
-  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -358,22 +464,33 @@ int esrp_conv3x3_nhwc(const esrp_conv3x3_t* desc, void* stream) {
   return run_conv(L, static_cast<cudaStream_t>(stream));
 }
 
-int64_t esrp_packed_conv3x3_bytes(int32_t num_chunks, int32_t kc, int32_t bn) {
-  return static_cast<int64_t>(num_chunks) * 9 * bn * kc * 2;
-}
-int64_t esrp_packed_conv1x1_bytes(int32_t num_chunks, int32_t kc, int32_t bn) {
-  return static_cast<int64_t>(num_chunks) * bn * kc * 2;
+int64_t esrp_packed_conv3x3_bytes(int32_t num_chunks, int32_t kc, int32_t bn, int32_t has_aux) {
+  return static_cast<int64_t>(num_chunks) * 3 * (has_aux ? 4 : 3) * bn * kc * 2;
 }
 
-int esrp_pack_conv3x3_weights(const float* w_oihw, int32_t cout, int32_t cin, int32_t kc, int32_t bn,
-                              int32_t num_chunks, const int32_t* chunk_lc0_host, void* out, void* stream) {
-  return pack_weights(w_oihw, cout, cin, 9, kc, bn, num_chunks, chunk_lc0_host, out,
-                      static_cast<cudaStream_t>(stream));
-}
-int esrp_pack_conv1x1_weights(const float* w_oi, int32_t cout, int32_t cin, int32_t kc, int32_t bn,
-                              int32_t num_chunks, const int32_t* chunk_lc0_host, void* out, void* stream) {
-  return pack_weights(w_oi, cout, cin, 1, kc, bn, num_chunks, chunk_lc0_host, out,
-                      static_cast<cudaStream_t>(stream));
+int esrp_pack_conv3x3_weights(const float* w_oihw, int32_t w_o, int32_t w_i, int32_t transpose, int32_t layout,
+                              int32_t row0, int32_t rows, int32_t kc, int32_t bn, int32_t num_chunks,
+                              const int32_t* chunk_lc0_host, const float* w_aux_oi, int32_t aux_cin,
+                              int32_t aux_chunks, void* out, void* stream) {
+  if (!w_oihw || !out || !chunk_lc0_host) return set_error("pack_weights: null pointer");
+  if (kc != 32 && kc != 64) return set_error("pack_weights: kc must be 32 or 64");
+  if (layout != ESRP_LAYOUT_TILE && layout != ESRP_LAYOUT_ROW) return set_error("pack_weights: unknown layout %d", layout);
+  if (bn != 16 && bn != 32 && bn != 64) return set_error("pack_weights: bn must be 16, 32 or 64");
+  if (rows < 1 || rows > bn || row0 < 0) return set_error("pack_weights: bad row slice row0=%d rows=%d bn=%d", row0, rows, bn);
+  if (num_chunks < 1 || num_chunks > ESRP_MAX_CHUNKS) return set_error("pack_weights: num_chunks=%d", num_chunks);
+  if (aux_chunks < 0 || aux_chunks > num_chunks || (aux_chunks > 0 && (!w_aux_oi || transpose)))
+    return set_error("pack_weights: bad conv1x1 arguments");
+  ChunkTable tab;
+  for (int i = 0; i < ESRP_MAX_CHUNKS; ++i) tab.lc0[i] = i < num_chunks ? chunk_lc0_host[i] : 0;
+  const int total = num_chunks * 3 * (aux_chunks > 0 ? 4 : 3) * bn * kc;
+  const int threads = 256;
+  int blocks = (total + threads - 1) / threads;
+  if (blocks > 1024) blocks = 1024;
+  pack_conv_weights_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      w_oihw, w_o, w_i, transpose, layout, row0, rows, kc, bn, num_chunks, tab, w_aux_oi, aux_cin, aux_chunks,
+      static_cast<__nv_bfloat16*>(out));
+  ESRP_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 int esrp_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int32_t n, int32_t c, int32_t h, int32_t w,

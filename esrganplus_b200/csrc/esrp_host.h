@@ -22,6 +22,7 @@ struct ConvLaunch {
   CUtensorMap tm0, tm1;
   ConvKParams params;
   int grid = 0;
+  int threads = 0;
   int smem = 0;
 };
 int plan_conv(const esrp_conv3x3_t& d, ConvLaunch* out);

@@ -14,6 +14,12 @@
 //   conv3: K = T_in | G[0:2gc]              -> G[2gc:3gc]   lrelu
 //   conv4: K = T_in | G[0:3gc]              -> G[3gc:4gc]   lrelu, + x2
 //   conv5: K = T_in | G[0:4gc]              -> T_out        0.2*(.) + x [noise] [RRDB: 0.2*(.) + x_rrdb]
+// Every launch computes at most 32 output channels (a 64-channel conv is two launches over disjoint
+// weight rows): all launches then share the N = 3*32 tap-stacked MMA shape and keep their weights
+// resident in shared memory.  With nf = 64 the K dimension is walked in 64-channel chunks (128-byte
+// swizzle); a chunk may cover growth channels that are not computed yet (e.g. conv2 reads G[0:64]
+// but only G[0:32] is x1) — their weights are packed as zeros, and G is zero-initialised so stale
+// values are always finite.
 // The residual trunk is carried in fp32 alongside its bf16 MMA-operand copy so that 69 chained
 // residual adds do not accumulate bf16 rounding.
 #include <cuda.h>
@@ -32,21 +38,20 @@ namespace esrp {
 namespace {
 
 struct ConvW {
-  // static description
-  int cin = 0, cout = 0;       // logical channels
+  int cin = 0, cout = 0;       // logical channels of the reference tensor [cout, cin, 3, 3]
+  int row0 = 0, rows = 0;      // output-channel slice this launch computes
   int kc = 0, bn = 0;
   int num_chunks = 0;
   int lc0[ESRP_MAX_CHUNKS] = {0};  // logical first input channel per chunk
   int aux_chunks = 0;              // leading chunks feeding the fused 1x1
   int w_idx = -1, b_idx = -1, aux_idx = -1;  // indices into the key list
-  // packed device storage (offsets into wbuf)
-  size_t w_off = 0, b_off = 0, aux_off = 0;
+  size_t w_off = 0, b_off = 0;     // packed device storage (offsets into wbuf)
+  int layout = -1;                 // ESRP_LAYOUT_* currently packed (-1: none)
 };
 
 struct Step {
   enum Kind { kConv, kPackInput, kUpsample } kind = kConv;
   ConvLaunch conv;
-  // elementwise steps
   const void* src = nullptr;
   void* dst = nullptr;
   int n = 0, h = 0, w = 0, c = 0, c_pad = 0;
@@ -57,24 +62,27 @@ struct Step {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-int bn_for(int cout) { return cout <= 16 ? 16 : (cout <= 32 ? 32 : 64); }
+int layout_for_width(int w) { return w > 64 ? ESRP_LAYOUT_ROW : ESRP_LAYOUT_TILE; }
 
 }  // namespace
 
 struct Rrdbnet {
-  int in_nc, out_nc, nf, nb, gc, upscale;
-  int in_pad;  // input channels padded to a multiple of 32
+  int in_nc, out_nc, nf, nb, gc, upscale, n_up;
+  int in_pad;  // input channels padded to 32
   std::vector<std::string> keys;
   std::vector<std::vector<int>> shapes;
-  // convs: fea, [nb][3][5] rdb convs, trunk, up1, up2, hr0, hr1
-  ConvW fea, trunk, up[2], hr0, hr1;
-  std::vector<ConvW> rdb;  // nb*3*5
+  // every logical conv is a list of <= 32-output-channel launches
+  std::vector<ConvW> fea, trunk, up[2], hr0, hr1;
+  std::vector<ConvW> rdb;  // nb*3*per_rdb: conv1..4, then conv5 as nf/32 output-channel slices
+  int per_rdb = 5;
   uint8_t* wbuf = nullptr;
   size_t wbytes = 0;
   bool weights_loaded = false;
+  std::vector<const void*> src_ptrs;  // borrowed fp32 tensors of the last load_weights (for re-layout)
   // plan cache (single entry: the common case is a fixed shape)
   int pn = 0, ph = 0, pw = 0, ptraining = -1;
   void* pws = nullptr;
+  bool g_zeroed = false;
   std::vector<Step> steps;
 };
 
@@ -86,23 +94,53 @@ int add_key(Rrdbnet* m, const std::string& k, std::vector<int> shape) {
   return static_cast<int>(m->keys.size()) - 1;
 }
 
-// Chunking of a conv whose logical input is [x: nf] ++ [growth: ng channels of G].
-void set_chunks(ConvW* c, int nf, int ng, int kc_pref) {
-  c->kc = kc_pref;
-  c->num_chunks = 0;
-  for (int ch = 0; ch < nf + ng; ch += c->kc) c->lc0[c->num_chunks++] = ch;
+// One logical conv [cout, cin, 3, 3] whose input is [x: nf_part] ++ [growth: ng_part channels of G],
+// cut into launches of <= 32 output channels.
+void define_conv(Rrdbnet* m, std::vector<ConvW>* out, const std::string& key, int cin, int cout, int nf_part,
+                 int ng_part, int aux_key = -1) {
+  ConvW c;
+  c.cin = cin;
+  c.cout = cout;
+  c.kc = (nf_part % 64 == 0) ? 64 : 32;
+  for (int ch = 0; ch < nf_part + ng_part; ch += c.kc) c.lc0[c.num_chunks++] = ch;
+  c.w_idx = add_key(m, key + ".weight", {cout, cin, 3, 3});
+  c.b_idx = add_key(m, key + ".bias", {cout});
+  if (aux_key >= 0) {
+    c.aux_idx = aux_key;
+    c.aux_chunks = nf_part / c.kc;  // the x chunks come first
+  }
+  for (int r0 = 0; r0 < cout; r0 += 32) {
+    c.row0 = r0;
+    c.rows = cout - r0 < 32 ? cout - r0 : 32;
+    c.bn = c.rows <= 16 ? 16 : 32;
+    out->push_back(c);
+  }
 }
 
-void define_conv(Rrdbnet* m, ConvW* c, const std::string& key, int cin, int cout, int nf_part, int ng_part,
-                 bool bias = true) {
-  c->cin = cin;
-  c->cout = cout;
-  c->bn = bn_for(cout);
-  // 64-wide chunks (128 B swizzle) when both segments are multiples of 64, else 32-wide (64 B swizzle)
-  const int kc = (nf_part % 64 == 0 && ng_part % 64 == 0) ? 64 : 32;
-  set_chunks(c, nf_part, ng_part, kc);
-  c->w_idx = add_key(m, key + ".weight", {cout, cin, 3, 3});
-  if (bias) c->b_idx = add_key(m, key + ".bias", {cout});
+int pack_one(Rrdbnet* m, ConvW* c, int layout, cudaStream_t s) {
+  const void* const* ptrs = m->src_ptrs.data();
+  const float* aux = c->aux_idx >= 0 ? static_cast<const float*>(ptrs[c->aux_idx]) : nullptr;
+  if (esrp_pack_conv3x3_weights(static_cast<const float*>(ptrs[c->w_idx]), c->cout, c->cin, 0, layout, c->row0,
+                                c->rows, c->kc, c->bn, c->num_chunks, c->lc0, aux, m->nf, c->aux_chunks,
+                                m->wbuf + c->w_off, s))
+    return 1;
+  ESRP_CUDA_OK(cudaMemsetAsync(m->wbuf + c->b_off, 0, static_cast<size_t>(c->bn) * 4, s));
+  ESRP_CUDA_OK(cudaMemcpyAsync(m->wbuf + c->b_off, static_cast<const float*>(ptrs[c->b_idx]) + c->row0,
+                               static_cast<size_t>(c->rows) * 4, cudaMemcpyDeviceToDevice, s));
+  c->layout = layout;
+  return 0;
+}
+
+template <class F>
+int for_each_conv(Rrdbnet* m, F&& f) {
+  for (auto& c : m->fea) if (f(&c)) return 1;
+  for (auto& c : m->rdb) if (f(&c)) return 1;
+  for (auto& c : m->trunk) if (f(&c)) return 1;
+  for (int u = 0; u < m->n_up; ++u)
+    for (auto& c : m->up[u]) if (f(&c)) return 1;
+  for (auto& c : m->hr0) if (f(&c)) return 1;
+  for (auto& c : m->hr1) if (f(&c)) return 1;
+  return 0;
 }
 
 }  // namespace
@@ -118,54 +156,39 @@ int esrp_rrdbnet_create(int32_t in_nc, int32_t out_nc, int32_t nf, int32_t nb, i
   if (nf % 32 || nf < 32 || nf > 64) return set_error("rrdbnet_create: nf=%d unsupported (32 or 64)", nf);
   if (gc != 32) return set_error("rrdbnet_create: gc=%d unsupported (the reference hard-codes gc=32, architecture.py:56)", gc);
   if (upscale != 4 && upscale != 2 && upscale != 1) return set_error("rrdbnet_create: upscale=%d unsupported (1, 2, 4)", upscale);
-  if (in_nc < 1 || in_nc > 64 || out_nc < 1 || out_nc > 64) return set_error("rrdbnet_create: in_nc/out_nc out of range");
+  if (in_nc < 1 || in_nc > 32 || out_nc < 1 || out_nc > 64) return set_error("rrdbnet_create: in_nc/out_nc out of range");
   if (nb < 1 || nb > 64) return set_error("rrdbnet_create: nb=%d out of range", nb);
   Rrdbnet* m = new Rrdbnet();
   m->in_nc = in_nc; m->out_nc = out_nc; m->nf = nf; m->nb = nb; m->gc = gc; m->upscale = upscale;
-  m->in_pad = (in_nc + 31) / 32 * 32;
-  const int n_up = upscale == 4 ? 2 : (upscale == 2 ? 1 : 0);
+  m->in_pad = 32;
+  m->n_up = upscale == 4 ? 2 : (upscale == 2 ? 1 : 0);
 
   // key order == reference state_dict order (sequential() flattening, block.py:95-108)
   define_conv(m, &m->fea, "model.0", in_nc, nf, m->in_pad, 0);
-  m->fea.cin = in_nc;
-  m->rdb.resize(static_cast<size_t>(nb) * 15);
+  m->per_rdb = 4 + nf / 32;
   for (int i = 0; i < nb; ++i) {
     for (int r = 0; r < 3; ++r) {
       const std::string p = "model.1.sub." + std::to_string(i) + ".RDB" + std::to_string(r + 1) + ".";
       const int aux_key = add_key(m, p + "conv1x1.weight", {gc, nf, 1, 1});
-      for (int k = 0; k < 5; ++k) {
-        ConvW* c = &m->rdb[(static_cast<size_t>(i) * 3 + r) * 5 + k];
-        define_conv(m, c, p + "conv" + std::to_string(k + 1) + ".0", nf + k * gc, k == 4 ? nf : gc, nf, k * gc);
-        if (k == 1) {
-          c->aux_idx = aux_key;
-          c->aux_chunks = nf / c->kc;  // the x chunks come first
-        }
-      }
+      for (int k = 0; k < 5; ++k)
+        define_conv(m, &m->rdb, p + "conv" + std::to_string(k + 1) + ".0", nf + k * gc, k == 4 ? nf : gc, nf, k * gc,
+                    k == 1 ? aux_key : -1);
     }
   }
   define_conv(m, &m->trunk, "model.1.sub." + std::to_string(nb), nf, nf, nf, 0);
-  for (int u = 0; u < n_up; ++u) define_conv(m, &m->up[u], "model." + std::to_string(3 + 3 * u), nf, nf, nf, 0);
-  define_conv(m, &m->hr0, "model." + std::to_string(2 + 3 * n_up), nf, nf, nf, 0);
-  define_conv(m, &m->hr1, "model." + std::to_string(4 + 3 * n_up), nf, out_nc, nf, 0);
+  for (int u = 0; u < m->n_up; ++u) define_conv(m, &m->up[u], "model." + std::to_string(3 + 3 * u), nf, nf, nf, 0);
+  define_conv(m, &m->hr0, "model." + std::to_string(2 + 3 * m->n_up), nf, nf, nf, 0);
+  define_conv(m, &m->hr1, "model." + std::to_string(4 + 3 * m->n_up), nf, out_nc, nf, 0);
 
   // packed weight storage
   size_t off = 0;
-  auto reserve = [&](ConvW* c) {
+  for_each_conv(m, [&](ConvW* c) {
     c->w_off = off;
-    off = align_up(off + static_cast<size_t>(esrp_packed_conv3x3_bytes(c->num_chunks, c->kc, c->bn)), 1024);
+    off = align_up(off + static_cast<size_t>(esrp_packed_conv3x3_bytes(c->num_chunks, c->kc, c->bn, c->aux_chunks > 0)), 1024);
     c->b_off = off;
     off = align_up(off + static_cast<size_t>(c->bn) * 4, 1024);
-    if (c->aux_idx >= 0) {
-      c->aux_off = off;
-      off = align_up(off + static_cast<size_t>(esrp_packed_conv1x1_bytes(c->aux_chunks, c->kc, c->bn)), 1024);
-    }
-  };
-  reserve(&m->fea);
-  for (auto& c : m->rdb) reserve(&c);
-  reserve(&m->trunk);
-  for (int u = 0; u < n_up; ++u) reserve(&m->up[u]);
-  reserve(&m->hr0);
-  reserve(&m->hr1);
+    return 0;
+  });
   m->wbytes = off;
   cudaError_t e = cudaMalloc(&m->wbuf, m->wbytes);
   if (e != cudaSuccess) {
@@ -207,31 +230,10 @@ int esrp_rrdbnet_load_weights(esrp_rrdbnet_t* h, const void* const* ptrs, int32_
     return set_error("rrdbnet_load_weights: expected %zu tensors, got %d", m->keys.size(), count);
   for (int i = 0; i < count; ++i)
     if (!ptrs[i]) return set_error("rrdbnet_load_weights: tensor %d (%s) is null", i, m->keys[i].c_str());
+  m->src_ptrs.assign(ptrs, ptrs + count);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  auto pack = [&](ConvW* c) -> int {
-    if (esrp_pack_conv3x3_weights(static_cast<const float*>(ptrs[c->w_idx]), c->cout, c->cin, c->kc, c->bn,
-                                  c->num_chunks, c->lc0, m->wbuf + c->w_off, stream))
-      return 1;
-    ESRP_CUDA_OK(cudaMemsetAsync(m->wbuf + c->b_off, 0, static_cast<size_t>(c->bn) * 4, s));
-    if (c->b_idx >= 0)
-      ESRP_CUDA_OK(cudaMemcpyAsync(m->wbuf + c->b_off, ptrs[c->b_idx], static_cast<size_t>(c->cout) * 4,
-                                   cudaMemcpyDeviceToDevice, s));
-    if (c->aux_idx >= 0) {
-      if (esrp_pack_conv1x1_weights(static_cast<const float*>(ptrs[c->aux_idx]), c->cout, m->nf, c->kc, c->bn,
-                                    c->aux_chunks, c->lc0, m->wbuf + c->aux_off, stream))
-        return 1;
-    }
-    return 0;
-  };
-  if (pack(&m->fea)) return 1;
-  for (auto& c : m->rdb)
-    if (pack(&c)) return 1;
-  if (pack(&m->trunk)) return 1;
-  const int n_up = m->upscale == 4 ? 2 : (m->upscale == 2 ? 1 : 0);
-  for (int u = 0; u < n_up; ++u)
-    if (pack(&m->up[u])) return 1;
-  if (pack(&m->hr0)) return 1;
-  if (pack(&m->hr1)) return 1;
+  // keep each conv in the layout its last plan asked for (ROW until a plan says otherwise)
+  if (for_each_conv(m, [&](ConvW* c) { return pack_one(m, c, c->layout < 0 ? ESRP_LAYOUT_ROW : c->layout, s); })) return 1;
   m->weights_loaded = true;
   return 0;
 }
@@ -279,14 +281,15 @@ void base_desc(const Rrdbnet* m, const ConvW& c, int n, int h, int w, esrp_conv3
   d->kc = c.kc;
   d->num_chunks = c.num_chunks;
   d->bn = c.bn;
-  d->cout = c.cout;
+  d->cout = c.rows;
   d->w_packed = m->wbuf + c.w_off;
+  d->w_layout = c.layout;
   d->bias = reinterpret_cast<const float*>(m->wbuf + c.b_off);
   d->s0 = 1.f; d->s1 = 1.f; d->s2 = 1.f;
   d->sigma = 0.1f;
 }
 
-int build_plan(Rrdbnet* m, int n, int h, int w, uint8_t* wsp, int training) {
+int build_plan(Rrdbnet* m, int n, int h, int w, uint8_t* wsp, int training, cudaStream_t stream) {
   m->steps.clear();
   const Workspace ws = layout(m, n, h, w);
   const int nf = m->nf, gc = m->gc;
@@ -300,6 +303,32 @@ int build_plan(Rrdbnet* m, int n, int h, int w, uint8_t* wsp, int training) {
     m->steps.push_back(st);
     return 0;
   };
+  // (re)pack a conv for the kernel decomposition its image width calls for
+  auto want = [&](std::vector<ConvW>& cs, int width) -> int {
+    const int lay = layout_for_width(width);
+    for (auto& c : cs)
+      if (c.layout != lay && pack_one(m, &c, lay, stream)) return 1;
+    return 0;
+  };
+  // plain single-source conv (all slices): src -> [bf16 out][f32 out][nchw out], optional fp32 residual
+  auto plain = [&](std::vector<ConvW>& cs, int hh, int ww, const void* src, int src_ct, int act, void* out_b,
+                   void* out_f, const void* r1_f32, bool to_y) -> int {
+    if (want(cs, ww)) return 1;
+    for (auto& c : cs) {
+      esrp_conv3x3_t d;
+      base_desc(m, c, n, hh, ww, &d);
+      d.src[0] = src; d.src_ctotal[0] = src_ct;
+      for (int i = 0; i < c.num_chunks; ++i) { d.chunk_src[i] = 0; d.chunk_c0[i] = c.lc0[i]; }
+      d.act = act;
+      if (r1_f32) { d.r1 = r1_f32; d.r1_is_f32 = 1; d.r1_ctotal = c.cout; d.r1_c0 = c.row0; d.s1 = 1.f; }
+      if (out_b) { d.out_bf16 = out_b; d.ob_ctotal = c.cout; d.ob_c0 = c.row0; }
+      if (out_f) { d.out_f32 = out_f; d.of_ctotal = c.cout; d.of_c0 = c.row0; }
+      if (to_y) d.out_nchw = reinterpret_cast<float*>(wsp);  // placeholder, patched per call
+      if (push_conv(d, to_y)) return 1;
+    }
+    return 0;
+  };
+
   // 0. NCHW fp32 -> NHWC bf16 (channels zero-padded to in_pad)
   {
     Step st;
@@ -308,20 +337,16 @@ int build_plan(Rrdbnet* m, int n, int h, int w, uint8_t* wsp, int training) {
     st.n = n; st.h = h; st.w = w; st.c = m->in_nc; st.c_pad = m->in_pad;
     m->steps.push_back(st);
   }
-  esrp_conv3x3_t d;
   // 1. fea_conv (architecture.py:55): no activation; bf16 + fp32 outputs
-  base_desc(m, m->fea, n, h, w, &d);
-  d.src[0] = wsp + ws.xin; d.src_ctotal[0] = m->in_pad;
-  for (int i = 0; i < m->fea.num_chunks; ++i) { d.chunk_src[i] = 0; d.chunk_c0[i] = m->fea.lc0[i]; }
-  d.out_bf16 = wsp + ws.fea_b; d.ob_ctotal = nf;
-  d.out_f32 = wsp + ws.fea_f; d.of_ctotal = nf;
-  if (push_conv(d)) return 1;
+  if (plain(m->fea, h, w, wsp + ws.xin, m->in_pad, 0, wsp + ws.fea_b, wsp + ws.fea_f, nullptr, false)) return 1;
 
   // 2. RRDB trunk
   // trunk buffer rotation: `cur` holds the current RDB input, `rr` the RRDB input (for block.py:291)
+  if (want(m->rdb, w)) return 1;
   const uint8_t* cur_b = wsp + ws.fea_b;
   const uint8_t* cur_f = wsp + ws.fea_f;
   int noise_index = 0;
+  esrp_conv3x3_t d;
   for (int i = 0; i < m->nb; ++i) {
     const uint8_t* rr_f = cur_f;
     for (int r = 0; r < 3; ++r) {
@@ -334,8 +359,8 @@ int build_plan(Rrdbnet* m, int n, int h, int w, uint8_t* wsp, int training) {
       uint8_t* out_b = wsp + ws.tb[slot];
       uint8_t* out_f = wsp + ws.tf[slot];
       uint8_t* G = wsp + ws.g;
-      for (int k = 0; k < 5; ++k) {
-        const ConvW& c = m->rdb[(static_cast<size_t>(i) * 3 + r) * 5 + k];
+      for (int k = 0; k < m->per_rdb; ++k) {
+        const ConvW& c = m->rdb[(static_cast<size_t>(i) * 3 + r) * m->per_rdb + k];
         base_desc(m, c, n, h, w, &d);
         d.src[0] = cur_b; d.src_ctotal[0] = nf;
         d.src[1] = G; d.src_ctotal[1] = 4 * gc;
@@ -344,50 +369,43 @@ int build_plan(Rrdbnet* m, int n, int h, int w, uint8_t* wsp, int training) {
           d.chunk_src[ch] = lc < nf ? 0 : 1;
           d.chunk_c0[ch] = lc < nf ? lc : lc - nf;
         }
-        if (k == 0 && c.num_chunks * c.kc == nf) d.src[1] = nullptr;
+        if (k == 0) d.src[1] = nullptr;
         if (k < 4) {
           d.act = 1;
           d.out_bf16 = G; d.ob_ctotal = 4 * gc; d.ob_c0 = k * gc;
-          if (k == 1) {  // x2 = lrelu(conv2) + conv1x1(x)   (block.py:262-263)
-            d.aux_chunks = c.aux_chunks;
-            d.w_aux = m->wbuf + c.aux_off;
-          }
+          if (k == 1) d.aux_chunks = c.aux_chunks;  // x2 = lrelu(conv2) + conv1x1(x)   (block.py:262-263)
           if (k == 3) {  // x4 = lrelu(conv4) + x2            (block.py:265-266)
             d.r1 = G; d.r1_is_f32 = 0; d.r1_ctotal = 4 * gc; d.r1_c0 = gc; d.s1 = 1.f;
           }
           if (push_conv(d)) return 1;
         } else {
-          // out = noise(0.2 * x5 + x)                         (block.py:268)
+          // out = noise(0.2 * x5 + x)                         (block.py:268), channels [row0, row0+32)
+          const int c0 = c.row0;
           d.act = 0; d.s0 = 0.2f;
-          d.r1 = cur_f; d.r1_is_f32 = 1; d.r1_ctotal = nf; d.r1_c0 = 0; d.s1 = 1.f;
-          d.noise = training ? 1 : 0;
+          d.r1 = cur_f; d.r1_is_f32 = 1; d.r1_ctotal = nf; d.r1_c0 = c0; d.s1 = 1.f;
+          d.noise = training ? 1 : 0; d.noise_ctotal = nf; d.noise_c0 = c0;
           if (r == 2) {  // RRDB: out * 0.2 + x                 (block.py:291)
-            d.r2 = rr_f; d.r2_is_f32 = 1; d.r2_ctotal = nf; d.r2_c0 = 0; d.s2 = 0.2f;
+            d.r2 = rr_f; d.r2_is_f32 = 1; d.r2_ctotal = nf; d.r2_c0 = c0; d.s2 = 0.2f;
           }
-          d.out_bf16 = out_b; d.ob_ctotal = nf;
-          d.out_f32 = out_f; d.of_ctotal = nf;
-          if (push_conv(d, false, training != 0, noise_index++)) return 1;
+          d.out_bf16 = out_b; d.ob_ctotal = nf; d.ob_c0 = c0;
+          d.out_f32 = out_f; d.of_ctotal = nf; d.of_c0 = c0;
+          if (push_conv(d, false, training != 0, noise_index)) return 1;
         }
       }
+      ++noise_index;
       cur_b = out_b;
       cur_f = out_f;
     }
   }
   // 3. LR_conv + shortcut (architecture.py:58,73; block.py:84-86)
-  base_desc(m, m->trunk, n, h, w, &d);
-  d.src[0] = cur_b; d.src_ctotal[0] = nf;
-  for (int i = 0; i < m->trunk.num_chunks; ++i) { d.chunk_src[i] = 0; d.chunk_c0[i] = m->trunk.lc0[i]; }
-  d.r1 = wsp + ws.fea_f; d.r1_is_f32 = 1; d.r1_ctotal = nf; d.s1 = 1.f;
-  d.out_bf16 = wsp + ws.u0; d.ob_ctotal = nf;
-  if (push_conv(d)) return 1;
+  if (plain(m->trunk, h, w, cur_b, nf, 0, wsp + ws.u0, nullptr, wsp + ws.fea_f, false)) return 1;
 
   // 4. upconv blocks: nearest x2 -> conv -> lrelu (block.py:315-322)
-  const int n_up = m->upscale == 4 ? 2 : (m->upscale == 2 ? 1 : 0);
   const uint8_t* feat = wsp + ws.u0;
   int ch_ = h, cw_ = w;
   uint8_t* hr[3] = {wsp + ws.hr_a, wsp + ws.hr_b, wsp + ws.hr_c};
   int hr_i = 0;
-  for (int u = 0; u < n_up; ++u) {
+  for (int u = 0; u < m->n_up; ++u) {
     Step st;
     st.kind = Step::kUpsample;
     st.src = feat;
@@ -395,32 +413,19 @@ int build_plan(Rrdbnet* m, int n, int h, int w, uint8_t* wsp, int training) {
     st.n = n; st.h = ch_; st.w = cw_; st.c = nf;
     m->steps.push_back(st);
     ch_ *= 2; cw_ *= 2;
-    base_desc(m, m->up[u], n, ch_, cw_, &d);
-    d.src[0] = hr[hr_i]; d.src_ctotal[0] = nf;
-    for (int i = 0; i < m->up[u].num_chunks; ++i) { d.chunk_src[i] = 0; d.chunk_c0[i] = m->up[u].lc0[i]; }
-    d.act = 1;
-    d.out_bf16 = hr[(hr_i + 1) % 3]; d.ob_ctotal = nf;
-    if (push_conv(d)) return 1;
+    if (plain(m->up[u], ch_, cw_, hr[hr_i], nf, 1, hr[(hr_i + 1) % 3], nullptr, nullptr, false)) return 1;
     feat = hr[(hr_i + 1) % 3];
     hr_i = (hr_i + 2) % 3;
   }
   // 5. HR_conv0 + lrelu (architecture.py:70)
-  base_desc(m, m->hr0, n, ch_, cw_, &d);
-  d.src[0] = feat; d.src_ctotal[0] = nf;
-  for (int i = 0; i < m->hr0.num_chunks; ++i) { d.chunk_src[i] = 0; d.chunk_c0[i] = m->hr0.lc0[i]; }
-  d.act = 1;
   uint8_t* hr0_out = hr[hr_i];
   if (hr0_out == feat) hr0_out = hr[(hr_i + 1) % 3];
-  d.out_bf16 = hr0_out; d.ob_ctotal = nf;
-  if (push_conv(d)) return 1;
+  if (plain(m->hr0, ch_, cw_, feat, nf, 1, hr0_out, nullptr, nullptr, false)) return 1;
   // 6. HR_conv1 (architecture.py:71): NCHW fp32 straight into the caller's output tensor
-  base_desc(m, m->hr1, n, ch_, cw_, &d);
-  d.src[0] = hr0_out; d.src_ctotal[0] = nf;
-  for (int i = 0; i < m->hr1.num_chunks; ++i) { d.chunk_src[i] = 0; d.chunk_c0[i] = m->hr1.lc0[i]; }
-  d.out_nchw = reinterpret_cast<float*>(wsp);  // placeholder, patched per call
-  if (push_conv(d, true)) return 1;
+  if (plain(m->hr1, ch_, cw_, hr0_out, nf, 0, nullptr, nullptr, nullptr, true)) return 1;
 
   m->pn = n; m->ph = h; m->pw = w; m->pws = wsp; m->ptraining = training;
+  m->g_zeroed = false;
   return 0;
 }
 
@@ -449,13 +454,20 @@ int esrp_rrdbnet_forward(esrp_rrdbnet_t* h, const float* x, float* y, int32_t n,
   const int64_t need = esrp_rrdbnet_workspace_bytes(h, n, hh, w);
   if (workspace_bytes < need) return set_error("rrdbnet_forward: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
   if (reinterpret_cast<uintptr_t>(workspace) % 1024) return set_error("rrdbnet_forward: workspace must be 1024-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (m->pn != n || m->ph != hh || m->pw != w || m->pws != workspace || m->ptraining != (training ? 1 : 0)) {
-    if (build_plan(m, n, hh, w, static_cast<uint8_t*>(workspace), training ? 1 : 0)) {
+    if (build_plan(m, n, hh, w, static_cast<uint8_t*>(workspace), training ? 1 : 0, s)) {
       m->pn = 0;
       return 1;
     }
   }
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!m->g_zeroed) {
+    // growth buffer: chunks may cover not-yet-written channels (zero weights) -> keep them finite
+    const Workspace ws = layout(m, n, hh, w);
+    ESRP_CUDA_OK(cudaMemsetAsync(static_cast<uint8_t*>(workspace) + ws.g, 0,
+                                 static_cast<size_t>(n) * hh * w * 4 * m->gc * 2, s));
+    m->g_zeroed = true;
+  }
   for (Step& st : m->steps) {
     switch (st.kind) {
       case Step::kPackInput:

@@ -27,9 +27,20 @@ extern "C" {
 
 #define ESRP_MAX_CHUNKS 8
 
-/* Kernel variant bits for esrp_conv3x3_t.variant (0 = library default). */
-#define ESRP_VARIANT_ALIGNED 1 /* 3 per-kx TMA boxes, atom-aligned UMMA operands (debug/safe)  */
-#define ESRP_VARIANT_MT1 2     /* one 16x8-pixel UMMA M-tile per CTA tile instead of two       */
+/* Tiling overrides for esrp_conv3x3_t.variant (0 = library default): bits 0-3 force the number
+ * of M-tile accumulator slots per CTA tile (1..5), bits 4-7 force log2 of the M-tile width in
+ * pixels (4..7).  Used by tests to exercise every tiling on small inputs. */
+#define ESRP_VARIANT_MT(mt) ((mt) & 15)
+#define ESRP_VARIANT_CWLOG2(l) (((l) & 15) << 4)
+
+/* Packed-weight layouts == kernel decompositions (esrp_conv3x3_t.w_layout, esrp_pack_conv3x3_weights):
+ *   ROW : one 128-pixel image row per M-tile, kernel rows ky stacked along N, column shift by
+ *         shifted shared-memory operands (conv3x3_row.cuh).  Best for images wider than ~64 px;
+ *         bn must be 16 or 32.
+ *   TILE: RM x CW pixel M-tiles, kernel columns kx stacked along N, column shift by warp shuffles
+ *         (conv3x3_tc.cuh).  Any width; the choice for narrow images (training crops). */
+#define ESRP_LAYOUT_TILE 0
+#define ESRP_LAYOUT_ROW 1
 
 /* One fused 3x3 / stride-1 / zero-pad-1 convolution over NHWC bf16 activations.
  * Replaces one `conv_block` call plus the torch.cat that feeds it and the elementwise ops that
@@ -53,8 +64,8 @@ typedef struct esrp_conv3x3 {
   int32_t aux_chunks;           /* leading chunks that also feed the 1x1 aux accumulator     */
   int32_t bn;                   /* padded Cout = UMMA N: 16, 32 or 64                        */
   int32_t cout;                 /* real Cout <= bn                                           */
-  const void* w_packed;         /* from esrp_pack_conv3x3_weights                            */
-  const void* w_aux;            /* from esrp_pack_conv1x1_weights, or NULL                   */
+  const void* w_packed;         /* from esrp_pack_conv3x3_weights (incl. the conv1x1 rows)   */
+  int32_t w_layout;             /* ESRP_LAYOUT_* the weights were packed for                 */
   const float* bias;            /* [bn] fp32 (zero padded), or NULL                          */
   int32_t act;                  /* 0 none, 1 LeakyReLU(0.2)                                  */
   float s0;
@@ -65,6 +76,7 @@ typedef struct esrp_conv3x3 {
   int32_t r2_is_f32, r2_ctotal, r2_c0;
   float s2;
   int32_t noise;                /* 1: multiplicative Gaussian noise (train mode)             */
+  int32_t noise_ctotal, noise_c0; /* Philox element index = pixel*noise_ctotal + noise_c0 + ch */
   float sigma;
   uint64_t seed, offset;        /* Philox key / per-call counter offset                      */
   void* out_bf16;               /* NHWC bf16 [n,h,w,ob_ctotal] written at ob_c0.. or NULL    */
@@ -73,6 +85,7 @@ typedef struct esrp_conv3x3 {
   int32_t of_ctotal, of_c0;
   float* out_nchw;              /* NCHW fp32 [n,cout,h,w], or NULL                           */
   int32_t variant;              /* ESRP_VARIANT_* bits                                       */
+  void* trace;                  /* NULL, or device int64[3*1024]: clock64 timeline of CTA 0  */
 } esrp_conv3x3_t;
 
 const char* esrp_last_error(void);
@@ -90,19 +103,24 @@ int esrp_sm_count(void);
 
 int esrp_conv3x3_nhwc(const esrp_conv3x3_t* desc, void* stream);
 
-/* Packed size in bytes of the weights for (num_chunks, kc, bn). */
-int64_t esrp_packed_conv3x3_bytes(int32_t num_chunks, int32_t kc, int32_t bn);
-int64_t esrp_packed_conv1x1_bytes(int32_t num_chunks, int32_t kc, int32_t bn);
+/* Packed size in bytes of the weights for (num_chunks, kc, bn); has_aux != 0 reserves the conv1x1
+ * rows (aux_chunks > 0 in the conv descriptor). */
+int64_t esrp_packed_conv3x3_bytes(int32_t num_chunks, int32_t kc, int32_t bn, int32_t has_aux);
 
-/* Repack reference-format weights (OIHW fp32, device) into UMMA B tiles.
- * chunk_lc0[i] = first *logical* input channel (index into dim 1 of w_oihw) of chunk i;
- * channels >= cin and rows >= cout are zero-filled. */
-int esrp_pack_conv3x3_weights(const float* w_oihw, int32_t cout, int32_t cin, int32_t kc,
-                              int32_t bn, int32_t num_chunks, const int32_t* chunk_lc0_host,
-                              void* out, void* stream);
-int esrp_pack_conv1x1_weights(const float* w_oi, int32_t cout, int32_t cin, int32_t kc, int32_t bn,
-                              int32_t num_chunks, const int32_t* chunk_lc0_host, void* out,
-                              void* stream);
+/* Repack reference-format weights (fp32 [w_o, w_i, 3, 3], device) into UMMA B tiles
+ * [chunk][ky][row = kx*bn + r (, 3*bn + r: conv1x1)][kc] (layout TILE; ROW swaps ky and kx),
+ * bf16, rows pre-swizzled.
+ *   transpose == 0 (forward operator):  row r, k  <-  W[row0 + r][lc0[chunk] + k][ky][kx]
+ *   transpose != 0 (data-gradient op):  row r, k  <-  W[lc0[chunk] + k][row0 + r][2-ky][2-kx]
+ * `rows` (<= bn) logical output channels starting at row0 are packed; indices outside the tensor
+ * are zero-filled.  chunk_lc0_host[i] = first logical input channel of chunk i.
+ * w_aux_oi: the bias-free 1x1 conv [w_o, aux_cin] (block.py:244,263) feeding the first aux_chunks
+ * chunks (forward only), or NULL with aux_chunks = 0. */
+int esrp_pack_conv3x3_weights(const float* w_oihw, int32_t w_o, int32_t w_i, int32_t transpose,
+                              int32_t layout, int32_t row0, int32_t rows, int32_t kc, int32_t bn,
+                              int32_t num_chunks,
+                              const int32_t* chunk_lc0_host, const float* w_aux_oi, int32_t aux_cin,
+                              int32_t aux_chunks, void* out, void* stream);
 
 /* Boundary layout converters (reference tensors are NCHW fp32, test_image/test.py:31-35). */
 int esrp_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int32_t n, int32_t c, int32_t h,

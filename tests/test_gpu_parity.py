@@ -5,7 +5,7 @@ Stated tolerances (DESIGN.md "Precision contract"): operands are rounded to bf16
 accumulated in fp32 in tensor memory, the residual trunk is carried in fp32.
   * one conv vs torch fp32 conv2d on the SAME bf16-rounded operands: fp32 outputs within
     2e-3 * max|ref| (accumulation order only), bf16 outputs within 1e-2 * max|ref| (one rounding).
-  * whole networks vs the fp32 reference: max|d| <= 3e-2 * std(ref) and PSNR >= 45 dB on the
+  * whole networks vs the fp32 reference: max|d| <= 6e-2 * std(ref) and PSNR >= 48 dB on the
     clamped [0,1] image (utils/util.py:107-114); the 8-bit PNG quantisation floor is 58.9 dB.
 """
 import ctypes as C
@@ -23,8 +23,8 @@ from oracle import esrgan_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-NET_REL_TOL = 3e-2
-NET_PSNR_DB = 45.0
+NET_REL_TOL = 6e-2
+NET_PSNR_DB = 48.0
 
 
 def _golden(golden_dir, name):
@@ -57,12 +57,27 @@ def _ref_conv(srcs, chunks, kc, w, bias, act):
     return F.leaky_relu(y, 0.2) if act else y
 
 
-@pytest.mark.parametrize("variant", [0, _lib.VARIANT_MT1, _lib.VARIANT_ALIGNED])
+# (n, h, w), variant: default tiling plus forced M-tile widths / accumulator-slot counts, so that the
+# x-halo column blocks (w > cw), every lane mapping (cw = 16..128) and partial tiles are all exercised
+TILINGS = [((2, 20, 27), 0), ((1, 16, 16), 0), ((3, 5, 7), 0), ((1, 33, 130), 0), ((1, 9, 300), 0),
+           ((2, 20, 27), _lib.variant_cwlog2(4)), ((2, 20, 27), _lib.variant_cwlog2(7) | _lib.variant_mt(2)),
+           ((1, 40, 64), _lib.variant_cwlog2(6) | _lib.variant_mt(1)), ((1, 40, 64), _lib.variant_cwlog2(5)),
+           ((2, 37, 128), _lib.variant_mt(3)), ((1, 128, 128), 0)]
+
+
+# row-streaming kernel: ragged widths/heights, multi-column images, single-row images, 3-slot TMEM ring
+ROW_TILINGS = [((2, 20, 27), 0), ((1, 16, 16), 0), ((3, 5, 7), 0), ((1, 33, 130), 0), ((1, 9, 300), 0),
+               ((2, 37, 128), _lib.variant_mt(3)), ((1, 128, 128), 0), ((2, 1, 140), 0), ((1, 2, 64), _lib.variant_mt(4))]
+ALL_TILINGS = [(_lib.LAYOUT_TILE, s, v) for s, v in TILINGS] + [(_lib.LAYOUT_ROW, s, v) for s, v in ROW_TILINGS]
+
+
 @pytest.mark.parametrize("kc,bn", [(64, 32), (64, 64), (32, 32), (32, 64), (64, 16), (32, 16)])
-@pytest.mark.parametrize("shape", [(2, 20, 27), (1, 16, 16), (3, 5, 7), (1, 33, 130)])
-def test_conv3x3_plain(cuda_dev, kc, bn, variant, shape):
+@pytest.mark.parametrize("layout,shape,variant", ALL_TILINGS)
+def test_conv3x3_plain(cuda_dev, kc, bn, layout, variant, shape):
     torch.backends.cudnn.allow_tf32 = False
     n, h, w = shape
+    if bn == 64 and (layout == _lib.LAYOUT_ROW or (variant & 15) > 2):
+        pytest.skip("TMEM: needs more accumulator slots of 192 columns than fit")
     g = torch.Generator(device=cuda_dev).manual_seed(kc * 1000 + bn * 10 + variant + h)
     s0 = torch.randn(n, h, w, 64, device=cuda_dev, generator=g).to(torch.bfloat16)
     s1 = torch.randn(n, h, w, 128, device=cuda_dev, generator=g).to(torch.bfloat16)
@@ -71,19 +86,19 @@ def test_conv3x3_plain(cuda_dev, kc, bn, variant, shape):
     cout = bn if bn >= 32 else 3
     wt = torch.randn(cout, cin, 3, 3, device=cuda_dev, generator=g) / (cin * 9) ** 0.5
     bias = torch.randn(cout, device=cuda_dev, generator=g)
-    wp = K.pack_conv3x3_weights(wt, kc, bn, [i * kc for i in range(len(chunks))])
+    wp = K.pack_conv3x3_weights(wt, kc, bn, [i * kc for i in range(len(chunks))], layout=layout)
     bias_p = torch.zeros(bn, device=cuda_dev)
     bias_p[:cout] = bias
     ref = _ref_conv([s0, s1], chunks, kc, wt, bias, act=1)
     scale = max(1.0, ref.abs().max().item())
     if cout < 16:  # Cout=3 tail conv (HR_conv1): NCHW fp32 output straight to the caller's tensor
         out = torch.full((n, cout, h, w), float("nan"), device=cuda_dev)
-        K.ConvCall(n=n, h=h, w=w, srcs=[s0, s1], kc=kc, chunks=chunks, bn=bn, cout=cout, w_packed=wp,
+        K.ConvCall(n=n, h=h, w=w, srcs=[s0, s1], kc=kc, chunks=chunks, bn=bn, cout=cout, w_packed=wp, w_layout=layout,
                    bias=bias_p, act=1, out_nchw=out, variant=variant).launch()
         assert (out - ref).abs().max().item() <= 2e-3 * scale
         return
     out = torch.full((n, h, w, 192), float("nan"), device=cuda_dev, dtype=torch.bfloat16)
-    K.ConvCall(n=n, h=h, w=w, srcs=[s0, s1], kc=kc, chunks=chunks, bn=bn, cout=cout, w_packed=wp,
+    K.ConvCall(n=n, h=h, w=w, srcs=[s0, s1], kc=kc, chunks=chunks, bn=bn, cout=cout, w_packed=wp, w_layout=layout,
                bias=bias_p, act=1, out_bf16=out, ob_c0=64, variant=variant).launch()
     got = out[..., 64:64 + cout].float().permute(0, 3, 1, 2)
     assert (got - ref).abs().max().item() <= 1e-2 * scale
@@ -91,12 +106,16 @@ def test_conv3x3_plain(cuda_dev, kc, bn, variant, shape):
     assert torch.isnan(out[..., :64].float()).all() and torch.isnan(out[..., 64 + cout:].float()).all()
 
 
-@pytest.mark.parametrize("kc,bn", [(64, 32), (32, 32), (64, 64)])
-def test_conv3x3_fused_epilogue(cuda_dev, kc, bn):
+@pytest.mark.parametrize("layout", [_lib.LAYOUT_TILE, _lib.LAYOUT_ROW])
+@pytest.mark.parametrize("kc,bn", [(64, 32), (32, 32), (64, 64), (32, 16)])
+@pytest.mark.parametrize("shape,variant", [((2, 20, 27), 0), ((1, 24, 128), 0), ((1, 6, 200), 0)])
+def test_conv3x3_fused_epilogue(cuda_dev, kc, bn, shape, variant, layout):
     """bias + LeakyReLU + s0 + conv1x1 aux + fp32 residual + bf16 RRDB residual, both output twins
     (block.py:262-268, 291)."""
-    n, h, w = 2, 20, 27
-    g = torch.Generator(device=cuda_dev).manual_seed(99 + kc + bn)
+    n, h, w = shape
+    if bn == 64 and layout == _lib.LAYOUT_ROW:
+        pytest.skip("row layout: bn <= 32")
+    g = torch.Generator(device=cuda_dev).manual_seed(99 + kc + bn + w)
     s0 = torch.randn(n, h, w, 64, device=cuda_dev, generator=g).to(torch.bfloat16)
     s1 = torch.randn(n, h, w, 128, device=cuda_dev, generator=g).to(torch.bfloat16)
     chunks = [(0, 0), (1, 64)] if kc == 64 else [(0, 0), (0, 32), (1, 32)]
@@ -104,15 +123,14 @@ def test_conv3x3_fused_epilogue(cuda_dev, kc, bn):
     wt = torch.randn(cout, cin, 3, 3, device=cuda_dev, generator=g) / (cin * 9) ** 0.5
     bias = torch.randn(cout, device=cuda_dev, generator=g)
     wa = torch.randn(cout, kc, 1, 1, device=cuda_dev, generator=g) / kc ** 0.5
-    wp = K.pack_conv3x3_weights(wt, kc, bn, [i * kc for i in range(len(chunks))])
-    wap = K.pack_conv1x1_weights(wa, kc, bn, [0])
+    wp = K.pack_conv3x3_weights(wt, kc, bn, [i * kc for i in range(len(chunks))], w_aux=wa, aux_chunks=1, layout=layout)
     r1 = torch.randn(n, h, w, 64, device=cuda_dev, generator=g)
     r2 = torch.randn(n, h, w, 64, device=cuda_dev, generator=g).to(torch.bfloat16)
     out_b = torch.zeros((n, h, w, 64), device=cuda_dev, dtype=torch.bfloat16)
     out_f = torch.zeros((n, h, w, 64), device=cuda_dev)
-    K.ConvCall(n=n, h=h, w=w, srcs=[s0, s1], kc=kc, chunks=chunks, bn=bn, cout=cout, w_packed=wp, bias=bias,
-               act=1, s0=0.5, w_aux=wap, aux_chunks=1, r1=r1, s1=0.25, r2=r2, s2=0.2, out_bf16=out_b,
-               out_f32=out_f).launch()
+    K.ConvCall(n=n, h=h, w=w, srcs=[s0, s1], kc=kc, chunks=chunks, bn=bn, cout=cout, w_packed=wp, w_layout=layout, bias=bias,
+               act=1, s0=0.5, aux_chunks=1, r1=r1, s1=0.25, r2=r2, s2=0.2, out_bf16=out_b,
+               out_f32=out_f, variant=variant).launch()
     ref = _ref_conv([s0, s1], chunks, kc, wt, bias, act=1)
     aux = F.conv2d(s0[..., :kc].float().permute(0, 3, 1, 2).contiguous(), wa.to(torch.bfloat16).float())
     v = 0.5 * ref + aux + 0.25 * r1[..., :cout].permute(0, 3, 1, 2)
@@ -122,9 +140,36 @@ def test_conv3x3_fused_epilogue(cuda_dev, kc, bn):
     assert (out_b[..., :cout].float().permute(0, 3, 1, 2) - v).abs().max().item() <= 1e-2 * scale
 
 
+@pytest.mark.parametrize("layout", [_lib.LAYOUT_TILE, _lib.LAYOUT_ROW])
+def test_conv3x3_output_channel_slices_and_transposed_pack(cuda_dev, layout):
+    """A 64-output conv issued as two 32-channel launches (how conv5 runs), and the data-gradient
+    operator packed from the same OIHW tensor (transpose=True) against conv_transpose2d."""
+    n, h, w = 1, 18, 40
+    g = torch.Generator(device=cuda_dev).manual_seed(5)
+    s0 = torch.randn(n, h, w, 64, device=cuda_dev, generator=g).to(torch.bfloat16)
+    wt = torch.randn(64, 64, 3, 3, device=cuda_dev, generator=g) / 24.0
+    out = torch.zeros((n, h, w, 64), device=cuda_dev)
+    for half in (0, 1):
+        wp = K.pack_conv3x3_weights(wt, 32, 32, [0, 32], row0=32 * half, rows=32, layout=layout)
+        K.ConvCall(n=n, h=h, w=w, srcs=[s0], kc=32, chunks=[(0, 0), (0, 32)], bn=32, cout=32, w_packed=wp,
+                   w_layout=layout, out_f32=out, of_c0=32 * half).launch()
+    x = s0.float().permute(0, 3, 1, 2).contiguous()
+    wq = wt.to(torch.bfloat16).float()
+    ref = F.conv2d(x, wq, padding=1)
+    assert (out.permute(0, 3, 1, 2) - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
+    # dgrad: dX = conv_transpose2d(dY, W) == conv(dY, W'[ci][co] flipped)
+    out2 = torch.zeros((n, h, w, 64), device=cuda_dev)
+    for half in (0, 1):
+        wpt = K.pack_conv3x3_weights(wt, 64, 32, [0], transpose=True, row0=32 * half, rows=32, layout=layout)
+        K.ConvCall(n=n, h=h, w=w, srcs=[s0], kc=64, chunks=[(0, 0)], bn=32, cout=32, w_packed=wpt, w_layout=layout,
+                   out_f32=out2, of_c0=32 * half).launch()
+    ref2 = F.conv_transpose2d(x, wq, padding=1)
+    assert (out2.permute(0, 3, 1, 2) - ref2).abs().max().item() <= 2e-3 * max(1.0, ref2.abs().max().item())
+
+
 def test_conv3x3_rejects_bad_arguments(cuda_dev):
     s0 = torch.zeros(1, 8, 8, 64, device=cuda_dev, dtype=torch.bfloat16)
-    wp = torch.zeros(9 * 32 * 64 * 2, device=cuda_dev, dtype=torch.uint8)
+    wp = torch.zeros(9 * 32 * 64 * 2, device=cuda_dev, dtype=torch.uint8)  # 3 ky x 96 rows x 64 ch bf16
     out = torch.zeros(1, 8, 8, 32, device=cuda_dev, dtype=torch.bfloat16)
     with pytest.raises(RuntimeError, match="kc"):
         K.ConvCall(n=1, h=8, w=8, srcs=[s0], kc=48, chunks=[(0, 0)], bn=32, cout=32, w_packed=wp, out_bf16=out).launch()
@@ -222,7 +267,7 @@ def test_train_mode_noise_matches_oracle_with_same_draws(cuda_dev):
         ref = O.rrdbnet_forward(x, sd, nb, training=True, noises=noises)
         ref_eval = O.rrdbnet_forward(x, sd, nb)
     _net_close(y, ref, "train-mode noise")
-    assert (ref - ref_eval).abs().max() > 10 * (y - ref).abs().max(), "noise must matter more than the tolerance"
+    assert (ref - ref_eval).abs().max() > 3 * (y - ref).abs().max(), "noise must matter more than the tolerance"
     # draws are N(0,1)
     z = torch.cat([t.flatten() for row in noises for t in row])
     assert abs(z.mean().item()) < 0.02 and abs(z.std().item() - 1.0) < 0.02

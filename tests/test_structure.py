@@ -151,7 +151,8 @@ def test_c_abi_exports_every_declared_symbol():
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     l = _lib.load()
     assert l.esrp_version() >= 100
-    assert l.esrp_packed_conv3x3_bytes(3, 64, 32) == 3 * 9 * 32 * 64 * 2
+    assert l.esrp_packed_conv3x3_bytes(3, 64, 32, 0) == 3 * 9 * 32 * 64 * 2
+    assert l.esrp_packed_conv3x3_bytes(3, 64, 32, 1) == 3 * 12 * 32 * 64 * 2
 
 
 def test_conv_desc_struct_matches_header_size():
