@@ -18,8 +18,8 @@
 //             the two halo rows per CTA are the only recomputation (~14 % at 14 rows per CTA).
 //   Stages  : one image row x one 64-channel chunk = 16.6 KB, so the ring is deep (up to 8 stages)
 //             and every dense-block conv keeps its weights resident in shared memory.
-//   Warps   : 0-7 epilogue (two warpgroups, each owning half of the output channels; TMEM lane quarter
-//             == warp % 4), 8 TMA producer, 9 MMA issuer / TMEM owner.
+//   Warps   : 0-11 epilogue = 3 warpgroups taking output rows round-robin (thread == pixel; TMEM lane
+//             quarter == warp % 4), 12 TMA producer, 13 MMA issuer / TMEM owner.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -33,7 +33,8 @@
 
 namespace esrp {
 
-constexpr int kRowEpiWarps = 8;
+constexpr int kRowWGs = 3;                     // epilogue warpgroups (rows in flight)
+constexpr int kRowEpiWarps = 4 * kRowWGs;
 constexpr int kRowThreads = 32 * (kRowEpiWarps + 2);
 constexpr int kRowTile = 128;  // output columns per M-tile
 constexpr int kMaxSlots = 8;
@@ -63,14 +64,16 @@ struct SegWalk {
 
 template <int GCH>
 __device__ __forceinline__ void tmem_ld_half(uint32_t taddr, uint32_t (&v)[GCH]) {
-  if constexpr (GCH == 16) {
+  if constexpr (GCH == 32) {
+    tmem_ld_x32(taddr, v);
+  } else if constexpr (GCH == 16) {
     tmem_ld_x16(taddr, v);
   } else {
     tmem_ld_x8(taddr, v);
   }
 }
 
-template <int KC, int BN>
+template <int KC, int BN, bool AUX>
 __global__ void __launch_bounds__(kRowThreads, 1)
 conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                    const __grid_constant__ ConvKParams p) {
@@ -78,7 +81,8 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
   constexpr uint32_t LAYOUT = (KC == 64) ? 2u : 4u;
   constexpr uint32_t SBO = 8 * RB;
   constexpr uint32_t DESC_HI = (SBO >> 4) | (1u << 14) | (LAYOUT << 29);
-  constexpr int GCH = BN / 2;  // output channels per epilogue warpgroup
+  constexpr int GC = BN < 16 ? BN : 16;  // output channels per epilogue round
+  constexpr int ROUNDS = BN / GC;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -90,11 +94,11 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
   uint64_t* q_empty = q_full + kMaxSlots;                   // [kMaxSlots]
   uint64_t* wfull = q_empty + kMaxSlots;                    // [1]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(wfull + 1);
+  float* bias_s = reinterpret_cast<float*>(smem + 1024);    // [BN]
 
-  const bool has_aux = p.aux_chunks > 0;
-  const int nb_rows = has_aux ? 4 * BN : 3 * BN;
-  const int w_block_bytes = nb_rows * RB;
-  const int w_chunk_bytes = 3 * w_block_bytes;
+  constexpr int nb_rows = AUX ? 4 * BN : 3 * BN;
+  constexpr int w_block_bytes = nb_rows * RB;
+  constexpr int w_chunk_bytes = 3 * w_block_bytes;
   const int w_res_bytes = p.w_resident ? p.num_chunks * w_chunk_bytes : 0;
   uint8_t* w_res = smem + kSmemFixed;
   uint8_t* stage0 = w_res + w_res_bytes;
@@ -116,7 +120,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     }
     for (int i = 0; i < kMaxSlots; ++i) {
       mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], 32 * kRowEpiWarps);
+      mbar_init(&q_empty[i], 12);  // 3 consuming output rows x 4 warps (weighted at segment ends)
     }
     mbar_init(wfull, 1);
     fence_barrier_init();
@@ -125,6 +129,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     tmem_alloc(tmem_holder, p.tmem_cols);
     tmem_relinquish();
   }
+  if (threadIdx.x < BN) bias_s[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -151,9 +156,14 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
             mbar_wait(&empty_bar[s], ph ^ 1);
             trace_ev(p, 0, tn);
             uint8_t* st = stage0 + static_cast<size_t>(s) * stage_bytes;
+            if (p.dbg & ESRP_DBG_NO_TMA) {
+              mbar_arrive(&full_bar[s]);
+              continue;
+            }
             mbar_arrive_expect_tx(&full_bar[s],
                                   static_cast<uint32_t>(p.a_box_bytes + (p.w_resident ? 0 : w_chunk_bytes)));
-            tma_load_4d(st, p.chunk_src[c] ? &tm1 : &tm0, &full_bar[s], p.chunk_c0[c], sw.x0 - 1, r, sw.img);
+            tma_load_4d(st, p.chunk_src[c] ? &tm1 : &tm0, &full_bar[s], p.chunk_c0[c],
+                        sw.x0 - ((p.dbg & ESRP_DBG_NO_XHALO) ? 0 : 1), r, sw.img);
             if (!p.w_resident)
               bulk_load_1d(st + a_bytes, p.w_packed + static_cast<size_t>(c) * w_chunk_bytes, w_chunk_bytes,
                            &full_bar[s]);
@@ -187,6 +197,14 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
           const uint32_t b_lo =
               umma_desc_lo(p.w_resident ? smem_u32(w_res + c * w_chunk_bytes) : smem_u32(st + a_bytes));
           const bool aux_c = c < p.aux_chunks;
+          if (p.dbg & ESRP_DBG_NO_MMA) {
+            if (elect_one()) {
+              mbar_arrive(&empty_bar[s]);
+              if (c == p.num_chunks - 1) mbar_arrive(&q_full[slot]);
+            }
+            __syncwarp();
+            continue;
+          }
           if (elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < 3; ++kk) {
@@ -210,112 +228,143 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     }
   } else {
     // ======================================= epilogue =======================================
-    const int wg = warp >> 2;                                   // channel half
+    // kRowWGs warpgroups take the output rows of a segment round-robin, so several rows are in flight
+    // (one warp per scheduler cannot hide the latency of this instruction stream on its own).
+    // Thread == pixel: it folds the three partial rows, applies the fused tail and stores all BN
+    // channels of its pixel, GC channels per round.
+    const int wg = warp >> 2;                                   // which rows
     const int q = warp & 3;                                     // TMEM lane quarter
     const int xl = q * 32 + lane;                               // column within the tile == TMEM lane
-    const int ch0 = wg * GCH;                                   // first output channel of this thread
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ch0;
-    float bias_r[GCH];
-#pragma unroll
-    for (int i = 0; i < GCH; ++i) bias_r[i] = p.bias ? __ldg(p.bias + ch0 + i) : 0.f;
-    uint32_t ri_base = 0, tn = 0;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t ri_base = 0, seen = 0, tn = 0;
     if (threadIdx.x == 0) trace_ev(p, 2, tn);
     SegWalk sw(p);
     while (sw.next(p)) {
       const int r0 = max(sw.ya - 1, 0), r1 = min(sw.yb, p.h - 1);
       const int xs = sw.x0 + xl;
-      const bool col_ok = xs < p.w && ch0 < p.cout;
+      const bool col_ok = xs < p.w;
 #pragma unroll 1
-      for (int y = sw.ya; y < sw.yb; ++y) {
+      for (int y = sw.ya + wg; y < sw.yb; y += kRowWGs) {
         const size_t pix = (static_cast<size_t>(sw.img) * p.h + y) * p.w + xs;
-        float r1v[GCH], r2v[GCH];
-        if (p.r1 && col_ok) load_residual<GCH>(p.r1, p.r1_is_f32, pix * p.r1_ctotal + p.r1_c0 + ch0, r1v);
-        if (p.r2 && col_ok) load_residual<GCH>(p.r2, p.r2_is_f32, pix * p.r2_ctotal + p.r2_c0 + ch0, r2v);
         const bool has_up = y - 1 >= r0, has_dn = y + 1 <= r1;
         const uint32_t i_mid = ri_base + (y - r0);
         const uint32_t i_last = has_dn ? i_mid + 1 : i_mid;
-        mbar_wait(&q_full[i_last % NS], (i_last / NS) & 1);
+        const uint32_t a_mid = lane_addr + (i_mid % NS) * NT;
+        const uint32_t a_up = lane_addr + ((i_mid - 1) % NS) * NT;
+        const uint32_t a_dn = lane_addr + ((i_mid + 1) % NS) * NT;
+        // Observe EVERY row's completion in order, also the rows other warpgroups consume: a parity wait
+        // is only meaningful if the waiter never skips a phase of that barrier.
+        for (; seen <= i_last; ++seen) mbar_wait(&q_full[seen % NS], (seen / NS) & 1);
         tcgen05_fence_after();
         if (threadIdx.x == 0) trace_ev(p, 2, tn);
-        uint32_t pu[GCH], pm[GCH], pd[GCH], ax[GCH];
-        const uint32_t a_mid = lane_addr + (i_mid % NS) * NT;
-        tmem_ld_half<GCH>(a_mid + 1 * BN, pm);
-        if (has_up) tmem_ld_half<GCH>(lane_addr + ((i_mid - 1) % NS) * NT + 0 * BN, pu);
-        if (has_dn) tmem_ld_half<GCH>(lane_addr + ((i_mid + 1) % NS) * NT + 2 * BN, pd);
-        if (has_aux) tmem_ld_half<GCH>(a_mid + 3 * BN, ax);
-        tmem_ld_wait();
-        // Q_{y-1} has now served outputs y-2, y-1, y: release it (and the tail rows at segment end)
-        tcgen05_fence_before();
-        if (has_up) mbar_arrive(&q_empty[(i_mid - 1) % NS]);
-        if (y == sw.yb - 1) {
-          mbar_arrive(&q_empty[i_mid % NS]);
-          if (has_dn) mbar_arrive(&q_empty[(i_mid + 1) % NS]);
+#pragma unroll
+        for (int g = 0; g < ROUNDS; ++g) {
+          const int ch0 = g * GC;
+          float r1v[GC], r2v[GC];
+          if (p.r1 && col_ok) load_residual<GC>(p.r1, p.r1_is_f32, pix * p.r1_ctotal + p.r1_c0 + ch0, r1v);
+          if (p.r2 && col_ok) load_residual<GC>(p.r2, p.r2_is_f32, pix * p.r2_ctotal + p.r2_c0 + ch0, r2v);
+          uint32_t pu[GC], pm[GC], pd[GC], ax[GC];
+          tmem_ld_half<GC>(a_mid + 1 * BN + ch0, pm);
+          if (has_up) tmem_ld_half<GC>(a_up + 0 * BN + ch0, pu);
+          if (has_dn) tmem_ld_half<GC>(a_dn + 2 * BN + ch0, pd);
+          if (AUX) tmem_ld_half<GC>(a_mid + 3 * BN + ch0, ax);
+          tmem_ld_wait();
+          if (g == ROUNDS - 1) {
+            // This output row has consumed its three accumulator rows.  Each slot is released by 3
+            // outputs x 4 warps = 12 arrivals; the first / last output of a segment also arrives for
+            // the neighbours that do not exist in it.  (tcgen05.wait::ld is warp-wide: lane 0 arrives.)
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              const int lo = (y == sw.ya) ? 1 : 0, hi = (y == sw.yb - 1) ? 1 : 0;
+              if (has_up) mbar_arrive_cnt(&q_empty[(i_mid - 1) % NS], 1 + 2 * lo);
+              mbar_arrive_cnt(&q_empty[i_mid % NS], 1 + lo + hi);
+              if (has_dn) mbar_arrive_cnt(&q_empty[(i_mid + 1) % NS], 1 + 2 * hi);
+            }
+          }
+          float v[GC];
+          const float4* bias4 = reinterpret_cast<const float4*>(bias_s + ch0);
+          if (has_up && has_dn) {
+#pragma unroll
+            for (int i = 0; i < GC; ++i) v[i] = (__uint_as_float(pm[i]) + __uint_as_float(pu[i])) + __uint_as_float(pd[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < GC; ++i) {
+              float a = __uint_as_float(pm[i]);
+              if (has_up) a += __uint_as_float(pu[i]);
+              if (has_dn) a += __uint_as_float(pd[i]);
+              v[i] = a;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < GC / 4; ++i) {
+            const float4 b4 = bias4[i];
+            v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+          }
+          if (p.act) {
+#pragma unroll
+            for (int i = 0; i < GC; ++i) v[i] = fmaxf(v[i], 0.2f * v[i]);  // LeakyReLU(0.2)
+          }
+          if (p.s0 != 1.0f) {
+#pragma unroll
+            for (int i = 0; i < GC; ++i) v[i] *= p.s0;
+          }
+          if (AUX) {
+#pragma unroll
+            for (int i = 0; i < GC; ++i) v[i] += __uint_as_float(ax[i]);
+          }
+          if (p.r1 && col_ok) {
+#pragma unroll
+            for (int i = 0; i < GC; ++i) v[i] = fmaf(p.s1, r1v[i], v[i]);
+          }
+          if (p.noise) {
+#pragma unroll 1
+            for (int i = 0; i < GC; i += 4) {
+              float z[4];
+              philox_normal4(p.seed,
+                             p.offset + (pix * static_cast<unsigned long long>(p.noise_ctotal) + p.noise_c0 + ch0 + i) / 4, z);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                // static register indexing: select the 4 values of this iteration
+#pragma unroll
+                for (int k = 0; k < GC; k += 4)
+                  if (k == i) v[k + j] = fmaf(z[j] * p.sigma, v[k + j], v[k + j]);
+              }
+            }
+          }
+          if (p.r2 && col_ok) {
+#pragma unroll
+            for (int i = 0; i < GC; ++i) v[i] = fmaf(p.s2, v[i], r2v[i]);
+          }
+          if (col_ok && ch0 < p.cout) {
+            if (p.out_bf16) {
+              uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.ob_ctotal + p.ob_c0 + ch0);
+#pragma unroll
+              for (int i = 0; i < GC / 8; ++i) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+                  pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
+                }
+                op[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
+            if (p.out_f32) {
+              float4* op = reinterpret_cast<float4*>(p.out_f32 + pix * p.of_ctotal + p.of_c0 + ch0);
+#pragma unroll
+              for (int i = 0; i < GC / 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+            if (p.out_nchw) {
+              const size_t plane = static_cast<size_t>(p.h) * p.w;
+              float* op = p.out_nchw + (static_cast<size_t>(sw.img) * p.cout) * plane + static_cast<size_t>(y) * p.w + xs;
+#pragma unroll
+              for (int i = 0; i < GC; ++i)
+                if (ch0 + i < p.cout) op[static_cast<size_t>(ch0 + i) * plane] = v[i];
+            }
+          }
         }
         if (threadIdx.x == 0) trace_ev(p, 2, tn);
-        if (!col_ok) continue;
-        float v[GCH];
-#pragma unroll
-        for (int i = 0; i < GCH; ++i) {
-          float a = __uint_as_float(pm[i]) + bias_r[i];
-          if (has_up) a += __uint_as_float(pu[i]);
-          if (has_dn) a += __uint_as_float(pd[i]);
-          v[i] = a;
-        }
-        if (p.act) {
-#pragma unroll
-          for (int i = 0; i < GCH; ++i) v[i] = lrelu02(v[i]);
-        }
-        if (p.s0 != 1.0f) {
-#pragma unroll
-          for (int i = 0; i < GCH; ++i) v[i] *= p.s0;
-        }
-        if (has_aux) {
-#pragma unroll
-          for (int i = 0; i < GCH; ++i) v[i] += __uint_as_float(ax[i]);
-        }
-        if (p.r1) {
-#pragma unroll
-          for (int i = 0; i < GCH; ++i) v[i] = fmaf(p.s1, r1v[i], v[i]);
-        }
-        if (p.noise) {
-#pragma unroll
-          for (int i = 0; i < GCH; i += 4) {
-            float z[4];
-            philox_normal4(p.seed,
-                           p.offset + (pix * static_cast<unsigned long long>(p.noise_ctotal) + p.noise_c0 + ch0 + i) / 4, z);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[i + j] = fmaf(z[j] * p.sigma, v[i + j], v[i + j]);
-          }
-        }
-        if (p.r2) {
-#pragma unroll
-          for (int i = 0; i < GCH; ++i) v[i] = fmaf(p.s2, v[i], r2v[i]);
-        }
-        if (p.out_bf16) {
-          uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.ob_ctotal + p.ob_c0 + ch0);
-#pragma unroll
-          for (int i = 0; i < GCH / 8; ++i) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
-              pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
-            }
-            op[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          }
-        }
-        if (p.out_f32) {
-          float4* op = reinterpret_cast<float4*>(p.out_f32 + pix * p.of_ctotal + p.of_c0 + ch0);
-#pragma unroll
-          for (int i = 0; i < GCH / 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        }
-        if (p.out_nchw) {
-          const size_t plane = static_cast<size_t>(p.h) * p.w;
-          float* op = p.out_nchw + (static_cast<size_t>(sw.img) * p.cout) * plane + static_cast<size_t>(y) * p.w + xs;
-#pragma unroll
-          for (int i = 0; i < GCH; ++i)
-            if (ch0 + i < p.cout) op[static_cast<size_t>(ch0 + i) * plane] = v[i];
-        }
       }
       ri_base += static_cast<uint32_t>(r1 - r0 + 1);
     }

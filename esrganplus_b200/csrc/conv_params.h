@@ -45,6 +45,7 @@ struct ConvKParams {
   float* out_f32;
   int of_ctotal, of_c0;
   float* out_nchw;
+  int dbg;           // timing experiments only (ESRP_DBG_*): results are wrong when non-zero
   long long* trace;  // optional [3][1024] clock64 timeline of CTA 0 (see trace_ev)
 };
 

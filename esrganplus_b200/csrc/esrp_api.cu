@@ -108,10 +108,11 @@ static void copy_common(const esrp_conv3x3_t& d, ConvKParams* pp) {
   p.out_f32 = static_cast<float*>(d.out_f32); p.of_ctotal = d.of_ctotal; p.of_c0 = d.of_c0;
   p.out_nchw = d.out_nchw;
   p.trace = static_cast<long long*>(d.trace);
+  p.dbg = d.variant & 0x700;
 }
 
 // ky-stacked row-streaming kernel (conv3x3_row.cuh)
-template <int KC, int BN>
+template <int KC, int BN, bool AUX>
 static int plan_row_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
   constexpr int RB = KC * 2;
   ConvKParams& p = out->params;
@@ -156,7 +157,7 @@ static int plan_row_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
   } else {
     out->tm1 = out->tm0;
   }
-  auto kern = conv3x3_row_kernel<KC, BN>;
+  auto kern = conv3x3_row_kernel<KC, BN, AUX>;
   static bool attr_set = false;
   if (!attr_set) {
     ESRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
@@ -299,10 +300,11 @@ int plan_conv(const esrp_conv3x3_t& d, ConvLaunch* out) {
   if ((d.out_bf16 || d.out_f32 || d.r1 || d.r2) && (d.cout % 16)) return set_error("conv3x3: NHWC outputs/residuals need cout %% 16 == 0");
   if (d.noise && ((d.noise_ctotal % 4) || (d.noise_c0 % 4) || d.noise_ctotal < d.cout)) return set_error("conv3x3: noise_ctotal/noise_c0 must be multiples of 4 and cover cout");
   if (d.w_layout == ESRP_LAYOUT_ROW) {
-    if (d.kc == 64 && d.bn == 16) return plan_row_t<64, 16>(d, out);
-    if (d.kc == 64 && d.bn == 32) return plan_row_t<64, 32>(d, out);
-    if (d.kc == 32 && d.bn == 16) return plan_row_t<32, 16>(d, out);
-    if (d.kc == 32 && d.bn == 32) return plan_row_t<32, 32>(d, out);
+    const bool aux = d.aux_chunks > 0;
+    if (d.kc == 64 && d.bn == 16) return aux ? plan_row_t<64, 16, true>(d, out) : plan_row_t<64, 16, false>(d, out);
+    if (d.kc == 64 && d.bn == 32) return aux ? plan_row_t<64, 32, true>(d, out) : plan_row_t<64, 32, false>(d, out);
+    if (d.kc == 32 && d.bn == 16) return aux ? plan_row_t<32, 16, true>(d, out) : plan_row_t<32, 16, false>(d, out);
+    if (d.kc == 32 && d.bn == 32) return aux ? plan_row_t<32, 32, true>(d, out) : plan_row_t<32, 32, false>(d, out);
     return set_error("conv3x3(row): unsupported kc=%d bn=%d (kc in {32,64}, bn in {16,32})", d.kc, d.bn);
   }
   if (d.w_layout != ESRP_LAYOUT_TILE) return set_error("conv3x3: unknown w_layout=%d", d.w_layout);

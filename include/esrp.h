@@ -32,6 +32,10 @@ extern "C" {
  * pixels (4..7).  Used by tests to exercise every tiling on small inputs. */
 #define ESRP_VARIANT_MT(mt) ((mt) & 15)
 #define ESRP_VARIANT_CWLOG2(l) (((l) & 15) << 4)
+/* Timing experiments (row kernel; the conv result is WRONG with any of these set). */
+#define ESRP_DBG_NO_XHALO 0x100 /* load boxes at x0 instead of x0-1 (no out-of-bounds on the left)  */
+#define ESRP_DBG_NO_MMA 0x200   /* TMA only: stages are released without issuing MMAs              */
+#define ESRP_DBG_NO_TMA 0x400   /* MMA only: stages are marked full without loading                 */
 
 /* Packed-weight layouts == kernel decompositions (esrp_conv3x3_t.w_layout, esrp_pack_conv3x3_weights):
  *   ROW : one 128-pixel image row per M-tile, kernel rows ky stacked along N, column shift by

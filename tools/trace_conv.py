@@ -50,7 +50,7 @@ def run(name, n=16, h=128, w=128, variant=0, iters=20):
     t0 = min(int(t[r][0]) for r in range(3) if int(t[r][0]) > 0)
     print(f"== {name} variant={variant} chunks={len(chunks)} kc={kc} bn={bn}")
     for r, role in enumerate(["producer(start, then after each empty-wait)", "mma(start; per chunk: full ok, issued)",
-                              "epilogue(start; per M-tile: acc_full ok, [per round: shifted], done)"]):
+                              "epilogue(start; per row: q_full ok, loaded+released, math done, stores issued)"]):
         ev = [int(v) - t0 for v in t[r] if int(v) > 0]
         print(role)
         print("  abs:", ev[:40])
