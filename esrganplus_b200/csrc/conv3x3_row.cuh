@@ -16,10 +16,10 @@
 //   Schedule: CTA b owns the contiguous output rows [b*U/G, (b+1)*U/G) (U = n * column blocks * H) and
 //             streams input rows ya-1 .. yb through a ring of TMEM slots (5 x 96 or 4 x 128 columns);
 //             the two halo rows per CTA are the only recomputation (~14 % at 14 rows per CTA).
-//   Stages  : one image row x one 64-channel chunk = 16.6 KB, so the ring is deep (up to 8 stages)
-//             and every dense-block conv keeps its weights resident in shared memory.
+//   Stages  : ring of row buffers (one image row x all K-chunks, 16.6 KB per 64-channel chunk); every
+//             dense-block conv keeps its weights resident in shared memory.  One tcgen05.commit per row.
 //   Warps   : 0-11 epilogue = 3 warpgroups taking output rows round-robin (thread == pixel; TMEM lane
-//             quarter == warp % 4), 12 TMA producer, 13 MMA issuer / TMEM owner.
+//             quarter == warp % 4), 12 TMA producer, 13-14 MMA issuers (input rows round-robin).
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -35,7 +35,8 @@ namespace esrp {
 
 constexpr int kRowWGs = 3;                     // epilogue warpgroups (rows in flight)
 constexpr int kRowEpiWarps = 4 * kRowWGs;
-constexpr int kRowThreads = 32 * (kRowEpiWarps + 2);
+constexpr int kRowMmaWarps = 2;                // MMA issuer warps (input rows round-robin)
+constexpr int kRowThreads = 32 * (kRowEpiWarps + 1 + kRowMmaWarps);
 constexpr int kRowTile = 128;  // output columns per M-tile
 constexpr int kMaxSlots = 8;
 
@@ -88,9 +89,8 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);   // [kMaxStages]
-  uint64_t* empty_bar = full_bar + kMaxStages;              // [kMaxStages]
-  uint64_t* q_full = empty_bar + kMaxStages;                // [kMaxSlots]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);   // [kMaxStages] one per row buffer
+  uint64_t* q_full = full_bar + kMaxStages;                 // [kMaxSlots]
   uint64_t* q_empty = q_full + kMaxSlots;                   // [kMaxSlots]
   uint64_t* wfull = q_empty + kMaxSlots;                    // [1]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(wfull + 1);
@@ -99,12 +99,12 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
   constexpr int nb_rows = AUX ? 4 * BN : 3 * BN;
   constexpr int w_block_bytes = nb_rows * RB;
   constexpr int w_chunk_bytes = 3 * w_block_bytes;
-  const int w_res_bytes = p.w_resident ? p.num_chunks * w_chunk_bytes : 0;
+  const int w_res_bytes = p.num_chunks * w_chunk_bytes;     // weights are always resident
   uint8_t* w_res = smem + kSmemFixed;
   uint8_t* stage0 = w_res + w_res_bytes;
-  const int a_bytes = p.a_stage_bytes;
-  const int stage_bytes = a_bytes + (p.w_resident ? 0 : w_chunk_bytes);
-  const int S = p.stages;
+  const int a_bytes = p.a_stage_bytes;                      // one chunk tile (TMA box rounded up to 1 KB)
+  const int row_bytes = a_bytes * p.num_chunks;             // one row buffer
+  const int D = p.stages;                                   // row buffers (< NS)
   const int NS = p.mt;  // TMEM slots
   const int NT = p.nt;
 
@@ -114,13 +114,12 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
   if (warp == kRowEpiWarps && lane == 0) {
     tma_prefetch_desc(&tm0);
     tma_prefetch_desc(&tm1);
-    for (int i = 0; i < S; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
-    }
+    for (int i = 0; i < D; ++i) mbar_init(&full_bar[i], 1);
     for (int i = 0; i < kMaxSlots; ++i) {
       mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], 12);  // 3 consuming output rows x 4 warps (weighted at segment ends)
+      // a slot is recycled after 3 consuming output rows x 4 warps have read it (weighted at segment ends)
+      // AND all 12 epilogue warps have observed its q_full phase (so none of them can be lapped)
+      mbar_init(&q_empty[i], 12 + kRowEpiWarps);
     }
     mbar_init(wfull, 1);
     fence_barrier_init();
@@ -137,95 +136,114 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
 
   if (warp == kRowEpiWarps) {
     // ===================================== TMA producer =====================================
+    // Row-buffer ring: buffer b = row % D holds the num_chunks K-chunk tiles of one input row.  A
+    // buffer is reused once the row that last occupied it has been fully multiplied, which the MMA
+    // warps signal on q_full (the same commit that wakes the epilogue): one commit per row in total.
     if (lane == 0) {
-      if (p.w_resident) {
-        mbar_arrive_expect_tx(wfull, static_cast<uint32_t>(w_res_bytes));
-        for (int c = 0; c < p.num_chunks; ++c)
-          bulk_load_1d(w_res + c * w_chunk_bytes, p.w_packed + static_cast<size_t>(c) * w_chunk_bytes,
-                       w_chunk_bytes, wfull);
-      }
-      uint32_t it = 0, tn = 0;
+      mbar_arrive_expect_tx(wfull, static_cast<uint32_t>(w_res_bytes));
+      for (int c = 0; c < p.num_chunks; ++c)
+        bulk_load_1d(w_res + c * w_chunk_bytes, p.w_packed + static_cast<size_t>(c) * w_chunk_bytes,
+                     w_chunk_bytes, wfull);
+      uint32_t tn = 0;
       trace_ev(p, 0, tn);
+      const int nch = p.num_chunks;
+      const uint32_t tx_bytes = static_cast<uint32_t>(p.a_box_bytes) * nch;
+      int b = 0;                 // row buffer of the row being loaded
+      uint32_t ri = 0;           // index of the row being loaded
+      int ds = 0;                // q_full slot of row ri - D (the row whose completion frees buffer b)
+      uint32_t dph = 0;
+      uint8_t* st = stage0;
       SegWalk sw(p);
       while (sw.next(p)) {
         const int r0 = max(sw.ya - 1, 0), r1 = min(sw.yb, p.h - 1);
-        for (int r = r0; r <= r1; ++r) {
-          for (int c = 0; c < p.num_chunks; ++c, ++it) {
-            const int s = it % S;
-            const uint32_t ph = (it / S) & 1;
-            mbar_wait(&empty_bar[s], ph ^ 1);
-            trace_ev(p, 0, tn);
-            uint8_t* st = stage0 + static_cast<size_t>(s) * stage_bytes;
-            if (p.dbg & ESRP_DBG_NO_TMA) {
-              mbar_arrive(&full_bar[s]);
-              continue;
-            }
-            mbar_arrive_expect_tx(&full_bar[s],
-                                  static_cast<uint32_t>(p.a_box_bytes + (p.w_resident ? 0 : w_chunk_bytes)));
-            tma_load_4d(st, p.chunk_src[c] ? &tm1 : &tm0, &full_bar[s], p.chunk_c0[c],
-                        sw.x0 - ((p.dbg & ESRP_DBG_NO_XHALO) ? 0 : 1), r, sw.img);
-            if (!p.w_resident)
-              bulk_load_1d(st + a_bytes, p.w_packed + static_cast<size_t>(c) * w_chunk_bytes, w_chunk_bytes,
-                           &full_bar[s]);
+        for (int r = r0; r <= r1; ++r, ++ri) {
+          if (ri >= static_cast<uint32_t>(D)) {
+            mbar_wait(&q_full[ds], dph);
+            if (++ds == NS) { ds = 0; dph ^= 1; }
           }
+          if (p.dbg & ESRP_DBG_NO_TMA) {
+            mbar_arrive(&full_bar[b]);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[b], tx_bytes);
+            for (int c = 0; c < nch; ++c)
+              tma_load_4d(st + c * a_bytes, p.chunk_src[c] ? &tm1 : &tm0, &full_bar[b], p.chunk_c0[c], sw.x0 - 1, r,
+                          sw.img);
+          }
+          st += row_bytes;
+          if (++b == D) { b = 0; st = stage0; }
         }
       }
+      trace_ev(p, 0, tn);
     }
-  } else if (warp == kRowEpiWarps + 1) {
-    // ====================================== MMA issuer ======================================
-    if (p.w_resident) mbar_wait(wfull, 0);
+  } else if (warp > kRowEpiWarps) {
+    // ====================================== MMA issuers ======================================
+    // kRowMmaWarps warps take the input rows round-robin.  tcgen05.mma issue is nearly synchronous
+    // (the tensor pipe queues only ~1-2 instructions), so with a single issuer every barrier wait /
+    // commit between two rows is a bubble in the pipe (measured: 85-99 cycles per N=96 MMA with one
+    // issuer, 57-61 with two; tools/ubench_row.cu).  Each warp stays converged and one elected lane
+    // issues, which keeps the MMA sequence on the uniform datapath.
+    const int mw = warp - (kRowEpiWarps + 1);
+    mbar_wait(wfull, 0);
     const uint32_t idesc_main = umma_idesc_bf16_m128(3 * BN);
     const uint32_t idesc_aux = umma_idesc_bf16_m128(4 * BN);
-    uint32_t it = 0, ri = 0, tn = 0;
-    if (lane == 0) trace_ev(p, 1, tn);
+    const int nch = p.num_chunks, naux = p.aux_chunks;
+    const uint32_t a_lo0 = umma_desc_lo(smem_u32(stage0));
+    const uint32_t w_lo0 = umma_desc_lo(smem_u32(w_res));
+    const uint32_t row_step = static_cast<uint32_t>(row_bytes) >> 4, chunk_step = static_cast<uint32_t>(a_bytes) >> 4;
+    constexpr uint32_t w_step = static_cast<uint32_t>(w_chunk_bytes) >> 4;
+    uint32_t tn = 0;
+    if (mw == 0 && lane == 0) trace_ev(p, 1, tn);
+    int b = 0, slot = 0, turn = 0;
+    uint32_t fph = 0, qph = 1;            // parities to wait on full[b] / q_empty[slot]
+    uint32_t a_lo = a_lo0, d_tmem = tmem_base;
     SegWalk sw(p);
     while (sw.next(p)) {
-      const int r0 = max(sw.ya - 1, 0), r1 = min(sw.yb, p.h - 1);
-      for (int r = r0; r <= r1; ++r, ++ri) {
-        const int slot = ri % NS;
-        const uint32_t qph = (ri / NS) & 1;
-        const uint32_t d_tmem = tmem_base + slot * NT;
-        for (int c = 0; c < p.num_chunks; ++c, ++it) {
-          const int s = it % S;
-          const uint32_t ph = (it / S) & 1;
-          mbar_wait(&full_bar[s], ph);
-          if (c == 0) mbar_wait(&q_empty[slot], qph ^ 1);
+      const int nrows = min(sw.yb, p.h - 1) - max(sw.ya - 1, 0) + 1;
+      for (int r = 0; r < nrows; ++r) {
+        // The ring lengths D (row buffers) and NS (TMEM slots) are multiples of kRowMmaWarps, so a buffer /
+        // slot only ever serves ONE issuer warp: each warp waits on its own barriers only and sees every
+        // phase of them in order.
+        if (turn == mw) {
+          mbar_wait(&full_bar[b], fph);
+          mbar_wait(&q_empty[slot], qph);
+        }
+        if (turn == mw) {
           tcgen05_fence_after();
-          if (lane == 0) trace_ev(p, 1, tn);
-          uint8_t* st = stage0 + static_cast<size_t>(s) * stage_bytes;
-          const uint32_t a_lo = umma_desc_lo(smem_u32(st));
-          const uint32_t b_lo =
-              umma_desc_lo(p.w_resident ? smem_u32(w_res + c * w_chunk_bytes) : smem_u32(st + a_bytes));
-          const bool aux_c = c < p.aux_chunks;
-          if (p.dbg & ESRP_DBG_NO_MMA) {
-            if (elect_one()) {
-              mbar_arrive(&empty_bar[s]);
-              if (c == p.num_chunks - 1) mbar_arrive(&q_full[slot]);
-            }
-            __syncwarp();
-            continue;
-          }
           if (elect_one()) {
+            if (p.dbg & ESRP_DBG_NO_MMA) {
+              mbar_arrive(&q_full[slot]);
+            } else {
+              uint32_t al = a_lo, bl = w_lo0;
+              for (int c = 0; c < nch; ++c) {
+                const bool aux_c = c < naux;
 #pragma unroll
-            for (int kk = 0; kk < 3; ++kk) {
-              const int kx = kk == 0 ? 1 : (kk == 1 ? 0 : 2);  // centre column first: it owns the conv1x1 columns
-              const uint32_t a_off = kx * RB;                  // A = the 130-pixel row shifted by kx pixels
-              const uint32_t b_off = kx * w_block_bytes;
-              const uint32_t idesc = (aux_c && kx == 1) ? idesc_aux : idesc_main;
+                for (int kk = 0; kk < 3; ++kk) {
+                  const int kx = kk == 0 ? 1 : (kk == 1 ? 0 : 2);  // centre column first: it owns the conv1x1 columns
+                  const uint32_t a_off = kx * RB;                  // A = the 130-pixel row shifted by kx pixels
+                  const uint32_t b_off = kx * w_block_bytes;
+                  const uint32_t idesc = (aux_c && kx == 1) ? idesc_aux : idesc_main;
 #pragma unroll
-              for (int ks = 0; ks < KC / 16; ++ks) {
-                umma_f16_ss2(d_tmem, a_lo + ((a_off + ks * 32) >> 4), DESC_HI, b_lo + ((b_off + ks * 32) >> 4),
-                             DESC_HI, idesc, (c | kk | ks) != 0 ? 1u : 0u);
+                  for (int ks = 0; ks < KC / 16; ++ks) {
+                    umma_f16_ss2(d_tmem, al + ((a_off + ks * 32) >> 4), DESC_HI, bl + ((b_off + ks * 32) >> 4),
+                                 DESC_HI, idesc, (c | kk | ks) != 0 ? 1u : 0u);
+                  }
+                }
+                al += chunk_step;
+                bl += w_step;
               }
+              umma_commit(&q_full[slot]);  // row complete: wakes the epilogue and frees the row buffer
             }
-            umma_commit(&empty_bar[s]);
-            if (c == p.num_chunks - 1) umma_commit(&q_full[slot]);
           }
           __syncwarp();
-          if (lane == 0) trace_ev(p, 1, tn);
         }
+        if (++turn == kRowMmaWarps) turn = 0;
+        a_lo += row_step;
+        if (++b == D) { b = 0; fph ^= 1; a_lo = a_lo0; }
+        d_tmem += NT;
+        if (++slot == NS) { slot = 0; qph ^= 1; d_tmem = tmem_base; }
       }
     }
+    if (mw == 0 && lane == 0) trace_ev(p, 1, tn);
   } else {
     // ======================================= epilogue =======================================
     // kRowWGs warpgroups take the output rows of a segment round-robin, so several rows are in flight
@@ -243,20 +261,39 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
       const int r0 = max(sw.ya - 1, 0), r1 = min(sw.yb, p.h - 1);
       const int xs = sw.x0 + xl;
       const bool col_ok = xs < p.w;
+      int turn = 0;
 #pragma unroll 1
-      for (int y = sw.ya + wg; y < sw.yb; y += kRowWGs) {
-        const size_t pix = (static_cast<size_t>(sw.img) * p.h + y) * p.w + xs;
+      for (int y = sw.ya; y < sw.yb; ++y) {
         const bool has_up = y - 1 >= r0, has_dn = y + 1 <= r1;
         const uint32_t i_mid = ri_base + (y - r0);
         const uint32_t i_last = has_dn ? i_mid + 1 : i_mid;
+        // Every warp walks EVERY output row and observes every q_full phase in order, also for the rows other
+        // warpgroups consume: a parity wait is only correct if the waiter checks phase k after phase k-1
+        // completed and before phase k+1 completes.  Each observation is acknowledged on q_empty, so a slot
+        // cannot be recycled (and its q_full phase advance) before all epilogue warps have seen it.
+        for (; seen <= i_last; ++seen) {
+          mbar_wait(&q_full[seen % NS], (seen / NS) & 1);
+          if (lane == 0) mbar_arrive(&q_empty[seen % NS]);  // "observed": see the q_empty count
+        }
+        const bool mine = turn == wg;
+        if (++turn == kRowWGs) turn = 0;
+        if (!mine) continue;
+        const size_t pix = (static_cast<size_t>(sw.img) * p.h + y) * p.w + xs;
         const uint32_t a_mid = lane_addr + (i_mid % NS) * NT;
         const uint32_t a_up = lane_addr + ((i_mid - 1) % NS) * NT;
         const uint32_t a_dn = lane_addr + ((i_mid + 1) % NS) * NT;
-        // Observe EVERY row's completion in order, also the rows other warpgroups consume: a parity wait
-        // is only meaningful if the waiter never skips a phase of that barrier.
-        for (; seen <= i_last; ++seen) mbar_wait(&q_full[seen % NS], (seen / NS) & 1);
         tcgen05_fence_after();
         if (threadIdx.x == 0) trace_ev(p, 2, tn);
+        if (p.dbg & ESRP_DBG_NO_EPI) {  // timing experiment: release the slots without reading them
+          __syncwarp();
+          if (lane == 0) {
+            const int lo = (y == sw.ya) ? 1 : 0, hi = (y == sw.yb - 1) ? 1 : 0;
+            if (has_up) mbar_arrive_cnt(&q_empty[(i_mid - 1) % NS], 1 + 2 * lo);
+            mbar_arrive_cnt(&q_empty[i_mid % NS], 1 + lo + hi);
+            if (has_dn) mbar_arrive_cnt(&q_empty[(i_mid + 1) % NS], 1 + 2 * hi);
+          }
+          continue;
+        }
 #pragma unroll
         for (int g = 0; g < ROUNDS; ++g) {
           const int ch0 = g * GC;

@@ -108,7 +108,7 @@ static void copy_common(const esrp_conv3x3_t& d, ConvKParams* pp) {
   p.out_f32 = static_cast<float*>(d.out_f32); p.of_ctotal = d.of_ctotal; p.of_c0 = d.of_c0;
   p.out_nchw = d.out_nchw;
   p.trace = static_cast<long long*>(d.trace);
-  p.dbg = d.variant & 0x700;
+  p.dbg = d.variant & 0xF00;
 }
 
 // ky-stacked row-streaming kernel (conv3x3_row.cuh)
@@ -127,7 +127,8 @@ static int plan_row_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
   if (ns > kMaxSlots) ns = kMaxSlots;
   const int force = d.variant & 15;
   if (force) ns = force;
-  if (ns < 3 || ns * p.nt > 512 || ns > kMaxSlots) return set_error("conv3x3(row): %d TMEM slots of %d columns unsupported", ns, p.nt);
+  ns -= ns % kRowMmaWarps;  // a slot must always serve the same issuer warp
+  if (ns < 4 || ns * p.nt > 512 || ns > kMaxSlots) return set_error("conv3x3(row): %d TMEM slots of %d columns unsupported", ns, p.nt);
   p.mt = ns;
   p.cw = kRowTile; p.cw_log2 = 7; p.rm = 1;
   p.x_tiles = (d.w + kRowTile - 1) / kRowTile;
@@ -137,19 +138,22 @@ static int plan_row_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
   if (p.units_total > 0x7fffffffLL) return set_error("conv3x3: problem too large (%lld rows)", p.units_total);
   p.a_box_bytes = (kRowTile + 2) * RB;
   p.a_stage_bytes = (p.a_box_bytes + 1023) / 1024 * 1024;
+  // row-buffer ring: D buffers of num_chunks tiles each, 2 <= D < TMEM slots (the producer learns that a
+  // buffer is free from the q_full phase of the row that used it, see conv3x3_row.cuh)
   const int avail = kMaxSmem - kSmemFixed - 1024;
-  const int s_res = w_all <= avail ? (avail - w_all) / p.a_stage_bytes : 0;
-  const int s_str = avail / (p.a_stage_bytes + w_chunk_bytes);
-  if (s_res >= 3) { p.w_resident = 1; p.stages = s_res; }
-  else if (s_str >= 2) { p.w_resident = 0; p.stages = s_str; }
-  else if (s_res >= 1) { p.w_resident = 1; p.stages = s_res; }
-  else return set_error("conv3x3(row): weights do not fit in shared memory (KC=%d BN=%d chunks=%d)", KC, BN, d.num_chunks);
-  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  const int row_bytes = p.a_stage_bytes * d.num_chunks;
+  int nbuf = w_all <= avail ? (avail - w_all) / row_bytes : 0;
+  if (nbuf > ns - 1) nbuf = ns - 1;
+  if (nbuf > kMaxStages) nbuf = kMaxStages;
+  nbuf -= nbuf % kRowMmaWarps;  // a buffer must always serve the same issuer warp
+  if (nbuf < 2)
+    return set_error("conv3x3(row): weights + 2 row buffers do not fit in shared memory (KC=%d BN=%d chunks=%d); split K", KC, BN, d.num_chunks);
+  p.w_resident = 1;
+  p.stages = nbuf;
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(p.mt * p.nt)) cols <<= 1;
   p.tmem_cols = cols;
-  out->smem = kSmemFixed + 1024 + (p.w_resident ? w_all : 0) +
-              p.stages * (p.a_stage_bytes + (p.w_resident ? 0 : w_chunk_bytes));
+  out->smem = kSmemFixed + 1024 + w_all + p.stages * row_bytes;
   copy_common(d, &p);
   if (make_nhwc_tmap(&out->tm0, d.src[0], d.n, d.h, d.w, d.src_ctotal[0], KC, kRowTile + 2, 1)) return 1;
   if (d.src[1]) {

@@ -26,6 +26,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -468,7 +469,20 @@ int esrp_rrdbnet_forward(esrp_rrdbnet_t* h, const float* x, float* y, int32_t n,
                                  static_cast<size_t>(n) * hh * w * 4 * m->gc * 2, s));
     m->g_zeroed = true;
   }
+  static const bool debug_sync = getenv("ESRP_DEBUG_SYNC") != nullptr;  // locate a failing launch
+  int step_idx = 0;
   for (Step& st : m->steps) {
+    if (debug_sync) {
+      cudaError_t e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) {
+        const Step& pr = m->steps[step_idx > 0 ? step_idx - 1 : 0];
+        return set_error("step %d (kind %d, n=%d h=%d w=%d chunks=%d aux=%d nt=%d slots=%d bufs=%d grid=%d threads=%d) failed: %s",
+                         step_idx - 1, (int)pr.kind, pr.conv.params.n, pr.conv.params.h, pr.conv.params.w,
+                         pr.conv.params.num_chunks, pr.conv.params.aux_chunks, pr.conv.params.nt, pr.conv.params.mt,
+                         pr.conv.params.stages, pr.conv.grid, pr.conv.threads, cudaGetErrorString(e));
+      }
+    }
+    ++step_idx;
     switch (st.kind) {
       case Step::kPackInput:
         if (esrp_nchw_f32_to_nhwc_bf16(x, st.dst, st.n, st.c, st.h, st.w, st.c_pad, stream)) return 1;

@@ -65,9 +65,10 @@ TILINGS = [((2, 20, 27), 0), ((1, 16, 16), 0), ((3, 5, 7), 0), ((1, 33, 130), 0)
            ((2, 37, 128), _lib.variant_mt(3)), ((1, 128, 128), 0)]
 
 
-# row-streaming kernel: ragged widths/heights, multi-column images, single-row images, 3-slot TMEM ring
+# row-streaming kernel: ragged widths/heights, multi-column images, single-row images, many segments per CTA
 ROW_TILINGS = [((2, 20, 27), 0), ((1, 16, 16), 0), ((3, 5, 7), 0), ((1, 33, 130), 0), ((1, 9, 300), 0),
-               ((2, 37, 128), _lib.variant_mt(3)), ((1, 128, 128), 0), ((2, 1, 140), 0), ((1, 2, 64), _lib.variant_mt(4))]
+               ((2, 37, 128), _lib.variant_mt(4)), ((1, 128, 128), 0), ((2, 1, 140), 0), ((1, 2, 64), _lib.variant_mt(4)),
+               ((6, 40, 128), 0), ((3, 70, 260), 0)]
 ALL_TILINGS = [(_lib.LAYOUT_TILE, s, v) for s, v in TILINGS] + [(_lib.LAYOUT_ROW, s, v) for s, v in ROW_TILINGS]
 
 
