@@ -134,7 +134,9 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  if (warp == kRowEpiWarps) {
+  if (p.dbg & ESRP_DBG_EMPTY) {
+    // timing experiment: prologue + teardown only
+  } else if (warp == kRowEpiWarps) {
     // ===================================== TMA producer =====================================
     // Row-buffer ring: buffer b = row % D holds the num_chunks K-chunk tiles of one input row.  A
     // buffer is reused once the row that last occupied it has been fully multiplied, which the MMA

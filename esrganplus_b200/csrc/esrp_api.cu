@@ -108,7 +108,7 @@ static void copy_common(const esrp_conv3x3_t& d, ConvKParams* pp) {
   p.out_f32 = static_cast<float*>(d.out_f32); p.of_ctotal = d.of_ctotal; p.of_c0 = d.of_c0;
   p.out_nchw = d.out_nchw;
   p.trace = static_cast<long long*>(d.trace);
-  p.dbg = d.variant & 0xF00;
+  p.dbg = d.variant & 0x1F00;
 }
 
 // ky-stacked row-streaming kernel (conv3x3_row.cuh)

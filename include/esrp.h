@@ -37,6 +37,7 @@ extern "C" {
 #define ESRP_DBG_NO_MMA 0x200   /* TMA only: stages are released without issuing MMAs              */
 #define ESRP_DBG_NO_TMA 0x400   /* MMA only: stages are marked full without loading                 */
 #define ESRP_DBG_NO_EPI 0x800   /* epilogue releases the accumulators without reading / storing     */
+#define ESRP_DBG_EMPTY 0x1000   /* kernel prologue + teardown only                                  */
 
 /* Packed-weight layouts == kernel decompositions (esrp_conv3x3_t.w_layout, esrp_pack_conv3x3_weights):
  *   ROW : one 128-pixel image row per M-tile, kernel rows ky stacked along N, column shift by
