@@ -123,13 +123,8 @@ static int plan_row_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
   const int w_chunk_bytes = 3 * nb_rows * RB;
   const int w_all = d.num_chunks * w_chunk_bytes;
   p.nt = nb_rows;
-  int ns = 512 / p.nt;
-  if (ns > kMaxSlots) ns = kMaxSlots;
-  const int force = d.variant & 15;
-  if (force) ns = force;
-  ns -= ns % kRowMmaWarps;  // a slot must always serve the same issuer warp
-  if (ns < 4 || ns * p.nt > 512 || ns > kMaxSlots) return set_error("conv3x3(row): %d TMEM slots of %d columns unsupported", ns, p.nt);
-  p.mt = ns;
+  const int nblk = has_aux ? 8 : 16;  // TMEM ring of output-row blocks (conv3x3_row.cuh)
+  p.mt = nblk;
   p.cw = kRowTile; p.cw_log2 = 7; p.rm = 1;
   p.x_tiles = (d.w + kRowTile - 1) / kRowTile;
   p.x_step = kRowTile;
@@ -138,21 +133,20 @@ static int plan_row_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
   if (p.units_total > 0x7fffffffLL) return set_error("conv3x3: problem too large (%lld rows)", p.units_total);
   p.a_box_bytes = (kRowTile + 2) * RB;
   p.a_stage_bytes = (p.a_box_bytes + 1023) / 1024 * 1024;
-  // row-buffer ring: D buffers of num_chunks tiles each, 2 <= D < TMEM slots (the producer learns that a
-  // buffer is free from the q_full phase of the row that used it, see conv3x3_row.cuh)
+  // row-buffer ring: D >= 2 buffers of num_chunks tiles each (the producer learns that a buffer is free
+  // from the block barrier of the output row its input completed, see conv3x3_row.cuh)
   const int avail = kMaxSmem - kSmemFixed - 1024;
   const int row_bytes = p.a_stage_bytes * d.num_chunks;
   int nbuf = w_all <= avail ? (avail - w_all) / row_bytes : 0;
-  if (nbuf > ns - 1) nbuf = ns - 1;
+  if (nbuf > nblk - 2) nbuf = nblk - 2;  // the producer must not be lapped on a block barrier
   if (nbuf > kMaxStages) nbuf = kMaxStages;
-  nbuf -= nbuf % kRowMmaWarps;  // a buffer must always serve the same issuer warp
+  const int force = d.variant & 15;
+  if (force && force < nbuf) nbuf = force;
   if (nbuf < 2)
     return set_error("conv3x3(row): weights + 2 row buffers do not fit in shared memory (KC=%d BN=%d chunks=%d); split K", KC, BN, d.num_chunks);
   p.w_resident = 1;
   p.stages = nbuf;
-  uint32_t cols = 32;
-  while (cols < static_cast<uint32_t>(p.mt * p.nt)) cols <<= 1;
-  p.tmem_cols = cols;
+  p.tmem_cols = 512;
   out->smem = kSmemFixed + 1024 + w_all + p.stages * row_bytes;
   copy_common(d, &p);
   if (make_nhwc_tmap(&out->tm0, d.src[0], d.n, d.h, d.w, d.src_ctotal[0], KC, kRowTile + 2, 1)) return 1;
