@@ -119,7 +119,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
   constexpr uint32_t LAYOUT = (KC == 64) ? 2u : 4u;
   constexpr uint32_t SBO = 8 * RB;
   constexpr uint32_t DESC_HI = (SBO >> 4) | (1u << 14) | (LAYOUT << 29);
-  constexpr int NBLK = AUX ? 8 : 16;                       // ring of output-row blocks (power of two)
+  constexpr int NBLK = (AUX || BN == 64) ? 8 : 16;         // ring of output-row blocks (power of two)
   constexpr int AUX_COL0 = NBLK * BN;                      // conv1x1 blocks live behind the main ring
   constexpr int nb_rows = AUX ? 4 * BN : 3 * BN;
   constexpr int w_block_bytes = nb_rows * RB;
@@ -169,7 +169,8 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     tmem_alloc(tmem_holder, 512);
     tmem_relinquish();
   }
-  if (threadIdx.x < BN) bias_s[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+  grid_dep_launch_dependents();
+  if (threadIdx.x < BN) bias_s[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;  // (weights: written long ago)
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -203,6 +204,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
                      w_chunk_bytes, wfull);
       uint32_t tn = 0;
       trace_ev(p, 0, tn);
+      grid_dep_wait();  // activations of the previous kernel must be complete before the first TMA load
       const int nch = p.num_chunks;
       const uint32_t tx_bytes = static_cast<uint32_t>(p.a_box_bytes) * nch;
       int b = 0;
@@ -331,6 +333,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     uint32_t O0 = 0, tn = 0;
     int turn = 0;
     if (threadIdx.x == 0) trace_ev(p, 2, tn);
+    grid_dep_wait();  // residual reads / output writes must not race with the previous kernel
     SegWalk sw(p);
     while (sw.next(p)) {
       const int r0 = max(sw.ya - 1, 0), r1 = min(sw.yb, p.h - 1);
@@ -356,37 +359,43 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
         }
         mbar_wait(&blk_full[pos(O)], use(O));
         tcgen05_fence_after();
-        uint32_t acc[ROUNDS][GC], ax[ROUNDS][GC];
-        if (real) {
+        if (!real) {  // dummy row at a segment end: just recycle the block
 #pragma unroll
-          for (int g = 0; g < ROUNDS; ++g) {
-            tmem_ld_cols<GC>(blk + g * GC, acc[g]);
-            if (AUX) tmem_ld_cols<GC>(blk + AUX_COL0 + g * GC, ax[g]);
+          for (int c = 0; c < BN; c += GC) {
+            if constexpr (GC == 16) tmem_st_zero_x16(blk + c); else tmem_st_zero_x8(blk + c);
           }
-          tmem_ld_wait();
+          tmem_st_wait();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&blk_empty[pos(O)]);
+          continue;
         }
-#pragma unroll
-        for (int c = 0; c < BN; c += GC) {
-          if constexpr (GC == 16) tmem_st_zero_x16(blk + c); else tmem_st_zero_x8(blk + c);
-        }
-        tmem_st_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&blk_empty[pos(O)]);
-        if (!store) continue;
+        // GC channels per round: load, zero, (after the last round: hand the block back), fused tail, store.
+        // The ring is 8-16 blocks deep, so releasing after the last load costs nothing.
 #pragma unroll
         for (int g = 0; g < ROUNDS; ++g) {
           const int ch0 = g * GC;
-          if (ch0 >= p.cout) continue;
+          uint32_t acc[GC], ax[GC];
+          tmem_ld_cols<GC>(blk + ch0, acc);
+          if (AUX) tmem_ld_cols<GC>(blk + AUX_COL0 + ch0, ax);
+          tmem_ld_wait();
+          if constexpr (GC == 16) tmem_st_zero_x16(blk + ch0); else tmem_st_zero_x8(blk + ch0);
+          if (g == ROUNDS - 1) {
+            tmem_st_wait();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&blk_empty[pos(O)]);
+          }
+          if (!store || ch0 >= p.cout) continue;
           float v[GC];
           const float4* bias4 = reinterpret_cast<const float4*>(bias_s + ch0);
 #pragma unroll
           for (int i = 0; i < GC / 4; ++i) {
             const float4 b4 = bias4[i];
-            v[4 * i] = __uint_as_float(acc[g][4 * i]) + b4.x;
-            v[4 * i + 1] = __uint_as_float(acc[g][4 * i + 1]) + b4.y;
-            v[4 * i + 2] = __uint_as_float(acc[g][4 * i + 2]) + b4.z;
-            v[4 * i + 3] = __uint_as_float(acc[g][4 * i + 3]) + b4.w;
+            v[4 * i] = __uint_as_float(acc[4 * i]) + b4.x;
+            v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + b4.y;
+            v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b4.z;
+            v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b4.w;
           }
           if (p.act) {
 #pragma unroll
@@ -398,7 +407,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
           }
           if (AUX) {
 #pragma unroll
-            for (int i = 0; i < GC; ++i) v[i] += __uint_as_float(ax[g][i]);
+            for (int i = 0; i < GC; ++i) v[i] += __uint_as_float(ax[i]);
           }
           if (p.r1) {
 #pragma unroll

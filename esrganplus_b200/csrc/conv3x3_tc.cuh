@@ -174,12 +174,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     tmem_alloc(tmem_holder, p.tmem_cols);
     tmem_relinquish();
   }
+  grid_dep_launch_dependents();
   if (threadIdx.x < BN) bias_s[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
   const int NT = p.nt;  // TMEM columns per M-tile accumulator
+  if (warp != 5) grid_dep_wait();  // producer (activation loads) and epilogue (residuals / stores)
 
   if (warp == 4) {
     // ===================================== TMA producer =====================================

@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -123,7 +124,8 @@ static int plan_row_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
   const int w_chunk_bytes = 3 * nb_rows * RB;
   const int w_all = d.num_chunks * w_chunk_bytes;
   p.nt = nb_rows;
-  const int nblk = has_aux ? 8 : 16;  // TMEM ring of output-row blocks (conv3x3_row.cuh)
+  const int nblk = (has_aux || BN == 64) ? 8 : 16;  // TMEM ring of output-row blocks (conv3x3_row.cuh)
+  if (has_aux && BN == 64) return set_error("conv3x3(row): bn=64 cannot carry the conv1x1 (TMEM)");
   p.mt = nblk;
   p.cw = kRowTile; p.cw_log2 = 7; p.rm = 1;
   p.x_tiles = (d.w + kRowTile - 1) / kRowTile;
@@ -272,7 +274,21 @@ int run_conv(const ConvLaunch& L, cudaStream_t stream) {
   if (L.grid < 1) return 0;
   void* args[3] = {const_cast<CUtensorMap*>(&L.tm0), const_cast<CUtensorMap*>(&L.tm1),
                    const_cast<ConvKParams*>(&L.params)};
-  ESRP_CUDA_OK(cudaLaunchKernel(L.kernel, dim3(L.grid), dim3(L.threads), args, L.smem, stream));
+  // Programmatic dependent launch: the kernel's prologue (barrier init, TMEM allocation + zeroing, weight
+  // fetch) may overlap the tail of the previous kernel in the stream; every kernel executes
+  // griddepcontrol.wait before it touches activations (esrp_ptx.cuh: grid_dep_wait).
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(L.grid);
+  cfg.blockDim = dim3(L.threads);
+  cfg.dynamicSmemBytes = L.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool no_pdl = getenv("ESRP_NO_PDL") != nullptr;
+  cfg.attrs = attr;
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  ESRP_CUDA_OK(cudaLaunchKernelExC(&cfg, L.kernel, args));
   return 0;
 }
 
@@ -303,7 +319,9 @@ int plan_conv(const esrp_conv3x3_t& d, ConvLaunch* out) {
     if (d.kc == 64 && d.bn == 32) return aux ? plan_row_t<64, 32, true>(d, out) : plan_row_t<64, 32, false>(d, out);
     if (d.kc == 32 && d.bn == 16) return aux ? plan_row_t<32, 16, true>(d, out) : plan_row_t<32, 16, false>(d, out);
     if (d.kc == 32 && d.bn == 32) return aux ? plan_row_t<32, 32, true>(d, out) : plan_row_t<32, 32, false>(d, out);
-    return set_error("conv3x3(row): unsupported kc=%d bn=%d (kc in {32,64}, bn in {16,32})", d.kc, d.bn);
+    if (d.kc == 64 && d.bn == 64) return plan_row_t<64, 64, false>(d, out);
+    if (d.kc == 32 && d.bn == 64) return plan_row_t<32, 64, false>(d, out);
+    return set_error("conv3x3(row): unsupported kc=%d bn=%d (kc in {32,64}, bn in {16,32,64})", d.kc, d.bn);
   }
   if (d.w_layout != ESRP_LAYOUT_TILE) return set_error("conv3x3: unknown w_layout=%d", d.w_layout);
   if (d.kc == 64) {

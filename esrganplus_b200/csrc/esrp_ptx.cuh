@@ -24,6 +24,20 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ----------------------------------------------------------------------------------------------
+// programmatic dependent launch
+// ----------------------------------------------------------------------------------------------
+// Allow the next kernel in the stream to start launching (its CTAs still need free SMs, and it must
+// itself wait before consuming our results).
+__device__ __forceinline__ void grid_dep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+}
+// Block until the prerequisite grid has completed and its memory operations are visible.  A no-op
+// when the kernel was launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void grid_dep_wait() {
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

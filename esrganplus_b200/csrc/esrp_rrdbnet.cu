@@ -14,9 +14,9 @@
 //   conv3: K = T_in | G[0:2gc]              -> G[2gc:3gc]   lrelu
 //   conv4: K = T_in | G[0:3gc]              -> G[3gc:4gc]   lrelu, + x2
 //   conv5: K = T_in | G[0:4gc]              -> T_out        0.2*(.) + x [noise] [RRDB: 0.2*(.) + x_rrdb]
-// Every launch computes at most 32 output channels (a 64-channel conv is two launches over disjoint
-// weight rows): all launches then share the N = 3*32 tap-stacked MMA shape and keep their weights
-// resident in shared memory.  With nf = 64 the K dimension is walked in 64-channel chunks (128-byte
+// Every dense-block launch computes at most 32 output channels (conv5 is two launches over disjoint
+// weight rows): they share the N = 3*32 tap-stacked MMA shape and keep their weights resident in shared
+// memory.  Single-chunk 64->64 convs (trunk, upconv, HR) run as one N = 3*64 launch.  With nf = 64 the K dimension is walked in 64-channel chunks (128-byte
 // swizzle); a chunk may cover growth channels that are not computed yet (e.g. conv2 reads G[0:64]
 // but only G[0:32] is x1) — their weights are packed as zeros, and G is zero-initialised so stale
 // values are always finite.
@@ -110,10 +110,13 @@ void define_conv(Rrdbnet* m, std::vector<ConvW>* out, const std::string& key, in
     c.aux_idx = aux_key;
     c.aux_chunks = nf_part / c.kc;  // the x chunks come first
   }
-  for (int r0 = 0; r0 < cout; r0 += 32) {
+  // <= 32 output channels per launch; a conv whose whole K is one chunk keeps 64 (its 3 x 192-row weight
+  // block still fits in shared memory, the MMA runs at N = 192 and the input is read once)
+  const int slice = (c.num_chunks == 1 && aux_key < 0) ? 64 : 32;
+  for (int r0 = 0; r0 < cout; r0 += slice) {
     c.row0 = r0;
-    c.rows = cout - r0 < 32 ? cout - r0 : 32;
-    c.bn = c.rows <= 16 ? 16 : 32;
+    c.rows = cout - r0 < slice ? cout - r0 : slice;
+    c.bn = c.rows <= 16 ? 16 : (c.rows <= 32 ? 32 : 64);
     out->push_back(c);
   }
 }
