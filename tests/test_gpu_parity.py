@@ -307,3 +307,17 @@ def test_config2_full_size_properties(cuda_dev):
     # one tile against the fp32 oracle at full tile size
     ref = O.rrdbnet_forward(x[3:4], sd, 23)
     _net_close(y1.cpu(), ref, "config 2 tile 3")
+
+
+def test_tiled_inference_matches_oracle_per_crop(cuda_dev):
+    """BASELINE config 3 in miniature: an LR image cut into independent crops (esrganplus_b200/tiled.py);
+    parity is per crop (zero padding at crop edges), exactly like running the reference on each crop."""
+    from esrganplus_b200 import tiled
+    sd = O.synth_state_dict_g(3, 3, 32, 2, seed=9)
+    net = _make(E.RRDBNet, sd, 32, 2, cuda_dev)
+    img = torch.rand(1, 3, 40, 72)
+    out = tiled.infer_tiled(lambda b: net(b.to(cuda_dev)).cpu(), img, 24)
+    assert out.shape == (1, 3, 160, 288)
+    for (y, x, th, tw) in tiled.crop_grid(40, 72, 24):
+        ref = O.rrdbnet_forward(img[:, :, y:y + th, x:x + tw], sd, 2)
+        _net_close(out[:, :, 4 * y:4 * (y + th), 4 * x:4 * (x + tw)], ref, f"crop {y},{x}")
