@@ -135,6 +135,12 @@ class Discriminator_VGG_128(nn.Module):
         self.features = _flat(*[B.layer_group(ci, co, k, s, norm_type=nt, act_type=act_type)
                                 for ci, co, k, s, nt in plan])
         self.classifier = nn.Sequential(nn.Linear(512 * 4 * 4, 100), nn.LeakyReLU(0.2, True), nn.Linear(100, 1))
+        object.__setattr__(self, "_engines", {})
+
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st["_engines"] = {}
+        return st
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if not x.is_cuda:

@@ -1,0 +1,160 @@
+// esrp_dnet.cu — the non-GEMM pieces of Discriminator_VGG_128 (reference: architecture.py:87-129):
+// space-to-depth for the 4x4 / stride-2 convs, BatchNorm2d batch statistics + normalise + LeakyReLU,
+// and the two small Linear layers.  The convolutions themselves run on the tcgen05 conv kernels
+// (esrp_conv3x3_nhwc); all kernels here are HBM-bound elementwise / reduction passes.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/esrp.h"
+#include "esrp_host.h"
+
+namespace esrp {
+
+// 4x4 stride-2 pad-1 conv == 2x2 conv over S[n, Y, X, (a*2+b)*c + ch] = in[n, 2Y+a-1, 2X+b-1, ch]
+// (Y in [0, h/2], X in [0, w/2], zero outside the image).  16-byte vectors along channels.
+__global__ void s2d_pad_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int n, int h, int w, int cv) {
+  const int ho = h / 2 + 1, wo = w / 2 + 1;
+  const size_t total = static_cast<size_t>(n) * ho * wo * 4 * cv;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % cv);
+    size_t t = i / cv;
+    const int ab = static_cast<int>(t % 4); t /= 4;
+    const int X = static_cast<int>(t % wo); t /= wo;
+    const int Y = static_cast<int>(t % ho);
+    const int img = static_cast<int>(t / ho);
+    const int y = 2 * Y + (ab >> 1) - 1, x = 2 * X + (ab & 1) - 1;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (y >= 0 && y < h && x >= 0 && x < w) val = __ldg(src + ((static_cast<size_t>(img) * h + y) * w + x) * cv + v);
+    dst[i] = val;
+  }
+}
+
+// Per-channel sum and sum of squares over the valid [h, w] region of x [n, hp, wp, c] fp32.
+// One block per (channel group of 32, pixel slab); partial sums via atomics on double accumulators.
+__global__ void bn_stats_kernel(const float* __restrict__ x, int n, int h, int w, int hp, int wp, int c,
+                                double* __restrict__ sums) {
+  const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int lane_px = threadIdx.x >> 5;            // 8 pixel lanes per block (256 threads)
+  const long long npx = static_cast<long long>(n) * h * w;
+  double s = 0.0, ss = 0.0;
+  if (ch < c) {
+    for (long long pi = static_cast<long long>(blockIdx.y) * 8 + lane_px; pi < npx; pi += static_cast<long long>(gridDim.y) * 8) {
+      const int xw = static_cast<int>(pi % w);
+      const long long t = pi / w;
+      const int yh = static_cast<int>(t % h);
+      const int img = static_cast<int>(t / h);
+      const float v = x[((static_cast<size_t>(img) * hp + yh) * wp + xw) * c + ch];
+      s += v;
+      ss += static_cast<double>(v) * v;
+    }
+  }
+  __shared__ double sh[2][8][32];
+  sh[0][lane_px][threadIdx.x & 31] = s;
+  sh[1][lane_px][threadIdx.x & 31] = ss;
+  __syncthreads();
+  if (lane_px == 0 && ch < c) {
+    for (int i = 1; i < 8; ++i) { s += sh[0][i][threadIdx.x & 31]; ss += sh[1][i][threadIdx.x & 31]; }
+    atomicAdd(&sums[ch], s);
+    atomicAdd(&sums[c + ch], ss);
+  }
+}
+
+// y = lrelu(x * scale[ch] + shift[ch]) over the valid region; writes NHWC bf16 [n,h,w,c] and/or the
+// NCHW-flattened fp32 [n, c*h*w] the classifier consumes (architecture.py:127 x.view(B, -1)).
+__global__ void bn_apply_kernel(const float* __restrict__ x, int n, int h, int w, int hp, int wp, int c,
+                                const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                                __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_nchw) {
+  const size_t total = static_cast<size_t>(n) * h * w * c;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % c);
+    size_t t = i / c;
+    const int xw = static_cast<int>(t % w); t /= w;
+    const int yh = static_cast<int>(t % h);
+    const int img = static_cast<int>(t / h);
+    float v = x[((static_cast<size_t>(img) * hp + yh) * wp + xw) * c + ch] * scale[ch] + shift[ch];
+    if (act) v = v > 0.f ? v : 0.2f * v;
+    if (out_bf16) out_bf16[i] = __float2bfloat16_rn(v);
+    if (out_nchw) out_nchw[((static_cast<size_t>(img) * c + ch) * h + yh) * w + xw] = v;
+  }
+}
+
+// y[b, o] = act(sum_k x[b, k] * W[o, k] + bias[o]); one warp per output.
+__global__ void linear_kernel(const float* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
+                              float* __restrict__ y, int b, int k, int o, int act) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= b * o) return;
+  const int bi = warp / o, oi = warp % o;
+  const float* xr = x + static_cast<size_t>(bi) * k;
+  const float* wr = wgt + static_cast<size_t>(oi) * k;
+  float acc = 0.f;
+  for (int i = lane; i < k; i += 32) acc = fmaf(xr[i], wr[i], acc);
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) {
+    float v = acc + (bias ? bias[oi] : 0.f);
+    if (act) v = v > 0.f ? v : 0.2f * v;
+    y[static_cast<size_t>(bi) * o + oi] = v;
+  }
+}
+
+}  // namespace esrp
+
+using namespace esrp;
+
+extern "C" {
+
+int esrp_s2d_pad_nhwc_bf16(const void* src, void* dst, int32_t n, int32_t h, int32_t w, int32_t c, void* stream) {
+  if (!src || !dst || (c % 8) || (h % 2) || (w % 2)) return set_error("s2d_pad: c %% 8, h %% 2, w %% 2 must be 0");
+  const int cv = c / 8;
+  const size_t total = static_cast<size_t>(n) * (h / 2 + 1) * (w / 2 + 1) * 4 * cv;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  s2d_pad_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(src),
+                                                                         static_cast<uint4*>(dst), n, h, w, cv);
+  ESRP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int esrp_bn_stats_nhwc_f32(const float* x, int32_t n, int32_t h, int32_t w, int32_t hp, int32_t wp, int32_t c,
+                           double* sums2c, void* stream) {
+  if (!x || !sums2c || h > hp || w > wp) return set_error("bn_stats: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ESRP_CUDA_OK(cudaMemsetAsync(sums2c, 0, sizeof(double) * 2 * c, s));
+  const long long npx = static_cast<long long>(n) * h * w;
+  int slabs = static_cast<int>((npx + 8 * 64 - 1) / (8 * 64));
+  if (slabs > 296) slabs = 296;
+  if (slabs < 1) slabs = 1;
+  dim3 grid((c + 31) / 32, slabs);
+  bn_stats_kernel<<<grid, 256, 0, s>>>(x, n, h, w, hp, wp, c, sums2c);
+  ESRP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int esrp_bn_apply_nhwc(const float* x, int32_t n, int32_t h, int32_t w, int32_t hp, int32_t wp, int32_t c,
+                       const float* scale, const float* shift, int32_t act, void* out_bf16, float* out_nchw_f32,
+                       void* stream) {
+  if (!x || !scale || !shift || (!out_bf16 && !out_nchw_f32)) return set_error("bn_apply: bad arguments");
+  const size_t total = static_cast<size_t>(n) * h * w * c;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  bn_apply_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, n, h, w, hp, wp, c, scale, shift, act, static_cast<__nv_bfloat16*>(out_bf16), out_nchw_f32);
+  ESRP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int esrp_linear_f32(const float* x, const float* w, const float* bias, float* y, int32_t b, int32_t k, int32_t o,
+                    int32_t act, void* stream) {
+  if (!x || !w || !y) return set_error("linear: null pointer");
+  const int warps = b * o;
+  const int blocks = (warps * 32 + 255) / 256;
+  linear_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, w, bias, y, b, k, o, act);
+  ESRP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

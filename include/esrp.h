@@ -138,6 +138,24 @@ int esrp_upsample2x_nhwc_bf16(const void* src, void* dst, int32_t n, int32_t h, 
                               int32_t c, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Discriminator_VGG_128 pieces (architecture.py:87-129).  The convolutions run on esrp_conv3x3_nhwc:
+ * a 4x4 / stride-2 / pad-1 conv is the 2x2 conv (3x3 with five zero taps) over the space-to-depth
+ * tensor produced here; BatchNorm2d (block.py:32) is statistics + a per-channel affine + LeakyReLU.
+ * ------------------------------------------------------------------------------------------- */
+/* dst[n, Y, X, (a*2+b)*c + ch] = src[n, 2Y+a-1, 2X+b-1, ch] (0 outside), Y <= h/2, X <= w/2; NHWC bf16. */
+int esrp_s2d_pad_nhwc_bf16(const void* src, void* dst, int32_t n, int32_t h, int32_t w, int32_t c, void* stream);
+/* sums2c[ch] = sum, sums2c[c+ch] = sum of squares over the valid [h,w] region of x [n,hp,wp,c] fp32. */
+int esrp_bn_stats_nhwc_f32(const float* x, int32_t n, int32_t h, int32_t w, int32_t hp, int32_t wp, int32_t c,
+                           double* sums2c, void* stream);
+/* y = [lrelu](x*scale[ch] + shift[ch]) over the valid region -> NHWC bf16 [n,h,w,c] and/or NCHW fp32. */
+int esrp_bn_apply_nhwc(const float* x, int32_t n, int32_t h, int32_t w, int32_t hp, int32_t wp, int32_t c,
+                       const float* scale, const float* shift, int32_t act, void* out_bf16,
+                       float* out_nchw_f32, void* stream);
+/* nn.Linear (+ optional LeakyReLU 0.2): y[b,o] = sum_k x[b,k] w[o,k] + bias[o]  (architecture.py:122-123). */
+int esrp_linear_f32(const float* x, const float* w, const float* bias, float* y, int32_t b, int32_t k, int32_t o,
+                    int32_t act, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * RRDBNet generator engine: what RRDBNet.forward / RRDB_Net.forward binds to
  * (architecture.py:76-78, test_image/architecture.py:36-38).  The handle owns the packed bf16
  * weight cache and per-shape launch plans; activations live in the caller's workspace.

@@ -321,3 +321,41 @@ def test_tiled_inference_matches_oracle_per_crop(cuda_dev):
     for (y, x, th, tw) in tiled.crop_grid(40, 72, 24):
         ref = O.rrdbnet_forward(img[:, :, y:y + th, x:x + tw], sd, 2)
         _net_close(out[:, :, 4 * y:4 * (y + th), 4 * x:4 * (x + tw)], ref, f"crop {y},{x}")
+
+
+# ---------------------------------------------------------------------------------------------------
+# Discriminator_VGG_128 forward (architecture.py:87-129) vs fixtures from the reference
+# ---------------------------------------------------------------------------------------------------
+def test_discriminator_forward_matches_reference_fixture(cuda_dev, golden_dir):
+    """Eval (running statistics) and train-mode (batch statistics + running-stat update) forward.  bf16
+    operands through ten conv layers: logits within 5e-2 * max(1, |ref|); BatchNorm running statistics are
+    fp32 reductions of fp32 conv outputs: within 2e-2 relative."""
+    g = _golden(golden_dir, "dvgg128.npz")
+    sd = O.synth_state_dict_d(3, 64, seed=41)
+    d = E.Discriminator_VGG_128(3, 64, norm_type="batch", act_type="leakyrelu", mode="CNA")
+    d.load_state_dict(sd, strict=True)
+    d = d.to(cuda_dev)
+    x = torch.from_numpy(g["x"]).to(cuda_dev)
+
+    def close(a, ref, what, tol):
+        ref = torch.from_numpy(np.asarray(ref))
+        err = (a.cpu() - ref).abs().max().item()
+        assert err <= tol * max(1.0, ref.abs().max().item()), f"{what}: {err:.3e} vs max {ref.abs().max().item():.3e}"
+
+    d.eval()
+    with torch.no_grad():
+        y = d(x)
+    assert y.shape == (4, 1)
+    close(y, g["y_eval"], "eval logits", 5e-2)
+    d.train()
+    with torch.no_grad():
+        yt = d(x)
+    close(yt, g["y_train"], "train logits", 5e-2)
+    after = d.state_dict()
+    for k, v in after.items():
+        if "running" in k:
+            close(v, g["after." + k], k, 2e-2)
+        elif "num_batches" in k:
+            assert int(v) == int(g["after." + k])
+    with pytest.raises(NotImplementedError):
+        d(x.requires_grad_(True))
