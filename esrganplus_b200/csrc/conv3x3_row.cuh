@@ -226,8 +226,8 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
           }
           mbar_arrive_expect_tx(&full_bar[b], tx_bytes);
           for (int c = 0; c < nch; ++c)
-            tma_load_4d(st + c * a_bytes, p.chunk_src[c] ? &tm1 : &tm0, &full_bar[b], p.chunk_c0[c], sw.x0 - 1, r,
-                        sw.img);
+            tma_load_4d_hint(st + c * a_bytes, p.chunk_src[c] ? &tm1 : &tm0, &full_bar[b], p.chunk_c0[c], sw.x0 - 1, r,
+                             sw.img, kL2EvictLast);  // bf16 activations are re-read by the next convs: keep in L2
           st += row_bytes;
           if (++b == D) { b = 0; st = stage0; }
         }
@@ -443,13 +443,14 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
                 const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * i + 2 * jj], v[8 * i + 2 * jj + 1]);
                 pk[jj] = *reinterpret_cast<const uint32_t*>(&h2);
               }
-              op[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              st_global_u4_hint(op + i, make_uint4(pk[0], pk[1], pk[2], pk[3]), kL2EvictLast);  // next conv's operand
             }
           }
           if (p.out_f32) {
             float4* op = reinterpret_cast<float4*>(p.out_f32 + pix * p.of_ctotal + p.of_c0 + ch0);
 #pragma unroll
-            for (int i = 0; i < GC / 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            for (int i = 0; i < GC / 4; ++i)  // fp32 trunk: read once, a whole dense block later -> stream
+              st_global_f4_hint(op + i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), kL2EvictFirst);
           }
           if (p.out_nchw) {
             const size_t plane = static_cast<size_t>(p.h) * p.w;

@@ -104,6 +104,36 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, ui
         "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// L2 eviction-priority policies (the encodings CUTLASS uses for TMA::CacheHintSm90).
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;  // streamed once: do not keep
+constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;   // re-read soon: keep
+__device__ __forceinline__ void tma_load_4d_hint(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1,
+                                                 int c2, int c3, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;\n"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)),
+        "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ float4 ld_global_f4_hint(const float4* p, uint64_t policy) {
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;\n"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(policy));
+  return v;
+}
+__device__ __forceinline__ void st_global_u4_hint(uint4* p, uint4 v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;\n" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void st_global_f4_hint(float4* p, float4 v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;\n" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w), "l"(policy)
+               : "memory");
+}
 // 1-D bulk copy global -> shared (size multiple of 16 B, both addresses 16 B aligned).
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes,
                                              uint64_t* bar) {
