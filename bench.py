@@ -199,6 +199,15 @@ def main_ours(args):
     flops_step = FLOP_PER_LR_PX * BATCH * TILE * TILE      # per GPU
     peak_tf, _hbm, peak_src = _peaks()
     achieved_tf = flops_step / (per_step * 1e-3) / 1e12
+    # DRAM traffic of the dominant kernel (conv3x3_row_kernel<64,32,0>: 345 of the 423 launches of a step),
+    # bytes per launch, from the committed ncu capture of this same workload (profiles/, null if absent)
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_launch_summary_config2.json")))
+        dom = max(prof["by_kernel"], key=lambda k: k["us"])
+        traffic = (dom["dram_read_MB"] + dom["dram_write_MB"]) * 1e6 / dom["launches"]
+    except Exception:
+        pass
 
     if rank == 0:
         cpu = None
@@ -219,7 +228,8 @@ def main_ours(args):
                     "d2h_bytes_per_step": y_host.numel() * 4 * world, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches * args.steps * world,
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved_tf / peak_tf, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read+write, dominant kernel)",
+                         "peak_source": peak_src,
                          "kernel": "conv3x3_row_kernel family (tcgen05 fused conv; all launches of the step but 3 layout kernels)",
                          "flops_per_step_per_gpu": flops_step},
             "cpu_baseline": cpu,
