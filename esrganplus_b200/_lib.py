@@ -63,7 +63,39 @@ class Conv3x3Desc(C.Structure):
         ("out_nchw", C.c_void_p),
         ("variant", C.c_int32),
         ("trace", C.c_void_p),
+        # training extensions
+        ("mask_out", C.c_void_p),
+        ("mask_out_ctotal", C.c_int32), ("mask_out_c0", C.c_int32),
+        ("mask_in", C.c_void_p),
+        ("mask_in_ctotal", C.c_int32), ("mask_in_c0", C.c_int32),
+        ("r2_pre", C.c_int32),
+        ("pre_bf16", C.c_void_p),
+        ("pb_ctotal", C.c_int32), ("pb_c0", C.c_int32),
+        ("pre_f32", C.c_void_p),
+        ("pf_ctotal", C.c_int32), ("pf_c0", C.c_int32),
     ]
+
+
+WGRAD_MAX_UNITS = 16
+
+
+class DgradGroup(C.Structure):
+    """Mirror of ``esrp_dgrad_group_t``."""
+    _fields_ = [("w", C.c_void_p), ("w_o", C.c_int32), ("w_i", C.c_int32), ("co0", C.c_int32), ("scale", C.c_float)]
+
+
+class WgradUnit(C.Structure):
+    """Mirror of ``esrp_wgrad_unit_t``."""
+    _fields_ = [("x", C.c_void_p), ("x_ctotal", C.c_int32), ("x_c0", C.c_int32),
+                ("dy", C.c_void_p), ("dy_ctotal", C.c_int32), ("dy_c0", C.c_int32),
+                ("acc", C.c_void_p), ("bias_acc", C.c_void_p)]
+
+
+class ScatterEntry(C.Structure):
+    """Mirror of ``esrp_scatter_entry_t``."""
+    _fields_ = [("acc", C.c_void_p), ("dst", C.c_void_p), ("dst_off", C.c_int64), ("dst_index", C.c_int32),
+                ("kind", C.c_int32), ("col0", C.c_int32), ("ncols", C.c_int32), ("nci", C.c_int32),
+                ("co0", C.c_int32), ("ci0", C.c_int32), ("w_i", C.c_int32), ("scale", C.c_float)]
 
 
 # name -> (restype, argtypes); the single source of truth for the symbols tests check.
@@ -91,6 +123,15 @@ SYMBOLS = {
                                      C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "esrp_linear_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int32, C.c_void_p]),
+    "esrp_pack_dgrad_weights": (C.c_int, [C.POINTER(DgradGroup), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_int32, C.c_void_p, C.c_void_p]),
+    "esrp_conv3x3_wgrad": (C.c_int, [C.POINTER(WgradUnit), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_void_p]),
+    "esrp_wgrad_scatter": (C.c_int, [C.POINTER(ScatterEntry), C.c_int32, C.c_void_p]),
+    "esrp_conv1x1_bwd": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "esrp_upsample2x_bwd_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                                C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "esrp_rrdbnet_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.POINTER(C.c_void_p)]),
     "esrp_rrdbnet_destroy": (None, [C.c_void_p]),

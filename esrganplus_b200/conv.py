@@ -86,6 +86,16 @@ class ConvCall:
     out_nchw: Optional[torch.Tensor] = None
     variant: int = 0
     trace: Optional[torch.Tensor] = None     # int64 [3*1024] device tensor (CTA 0 timeline)
+    # training extensions (include/esrp.h): masks are int16 tensors [n,h,w,bits/16]
+    mask_out: Optional[torch.Tensor] = None
+    mask_out_c0: int = 0
+    mask_in: Optional[torch.Tensor] = None
+    mask_in_c0: int = 0
+    r2_pre: int = 0
+    pre_bf16: Optional[torch.Tensor] = None
+    pb_c0: int = 0
+    pre_f32: Optional[torch.Tensor] = None
+    pf_c0: int = 0
     _keep: list = field(default_factory=list, repr=False)
 
     def desc(self) -> Conv3x3Desc:
@@ -129,6 +139,20 @@ class ConvCall:
             d.out_nchw = self.out_nchw.data_ptr()
         d.variant = self.variant
         d.trace = self.trace.data_ptr() if self.trace is not None else None
+        for name in ("mask_out", "mask_in"):
+            t = getattr(self, name)
+            if t is not None:
+                assert t.is_cuda and t.dtype == torch.int16 and t.is_contiguous() and t.shape[:3] == (self.n, self.h, self.w)
+                setattr(d, name, t.data_ptr())
+                setattr(d, name + "_ctotal", t.shape[3] * 16)
+                setattr(d, name + "_c0", getattr(self, name + "_c0"))
+        d.r2_pre = self.r2_pre
+        if self.pre_bf16 is not None:
+            assert self.pre_bf16.dtype == torch.bfloat16 and self.pre_bf16.is_contiguous()
+            d.pre_bf16, d.pb_ctotal, d.pb_c0 = self.pre_bf16.data_ptr(), self.pre_bf16.shape[3], self.pb_c0
+        if self.pre_f32 is not None:
+            assert self.pre_f32.dtype == torch.float32 and self.pre_f32.is_contiguous()
+            d.pre_f32, d.pf_ctotal, d.pf_c0 = self.pre_f32.data_ptr(), self.pre_f32.shape[3], self.pf_c0
         return d
 
     def launch(self) -> None:
@@ -166,3 +190,81 @@ def upsample2x_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
     _lib.check(lib.esrp_upsample2x_nhwc_bf16(x.data_ptr(), out.data_ptr(), n, h, w, c, _stream_ptr()),
                "esrp_upsample2x_nhwc_bf16")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# backward-pass helpers (esrp_pack_dgrad_weights / esrp_conv3x3_wgrad / ... in include/esrp.h)
+# ------------------------------------------------------------------------------------------------
+def pack_dgrad_weights(groups: Sequence[Optional[tuple]], row0: int, rows: int, kc: int, bn: int,
+                       layout: int = _lib.LAYOUT_TILE) -> torch.Tensor:
+    """groups: per 32-channel K group either None (zero weights) or (w_oihw fp32 cuda, co0, scale)."""
+    lib = _lib.load()
+    arr = (_lib.DgradGroup * len(groups))()
+    keep = []
+    dev = None
+    for i, g in enumerate(groups):
+        if g is None:
+            continue
+        w, co0, scale = g
+        assert w.is_cuda and w.dtype == torch.float32 and w.dim() == 4 and w.shape[2:] == (3, 3)
+        w = w.contiguous()
+        keep.append(w)
+        dev = w.device
+        arr[i].w, arr[i].w_o, arr[i].w_i, arr[i].co0, arr[i].scale = w.data_ptr(), w.shape[0], w.shape[1], co0, scale
+    chunks = (len(groups) * 32 + kc - 1) // kc
+    out = torch.empty(lib.esrp_packed_conv3x3_bytes(chunks, kc, bn, 0), dtype=torch.uint8, device=dev)
+    _lib.check(lib.esrp_pack_dgrad_weights(arr, len(groups), layout, row0, rows, kc, bn, out.data_ptr(), _stream_ptr()),
+               "esrp_pack_dgrad_weights")
+    return out
+
+
+def conv3x3_wgrad(units: Sequence[tuple], n: int, h: int, w: int, splits: int = 0) -> None:
+    """units: (x bf16 NHWC, x_c0, dy bf16 NHWC, dy_c0, acc fp32 [9,64,32], bias_acc fp32 [64] or None)."""
+    lib = _lib.load()
+    arr = (_lib.WgradUnit * len(units))()
+    for i, (x, x_c0, dy, dy_c0, acc, bacc) in enumerate(units):
+        assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and x.is_contiguous() and dy.is_contiguous()
+        assert acc.dtype == torch.float32 and acc.is_contiguous() and acc.numel() == 9 * 64 * 32
+        arr[i].x, arr[i].x_ctotal, arr[i].x_c0 = x.data_ptr(), x.shape[3], x_c0
+        arr[i].dy, arr[i].dy_ctotal, arr[i].dy_c0 = dy.data_ptr(), dy.shape[3], dy_c0
+        arr[i].acc = acc.data_ptr()
+        arr[i].bias_acc = bacc.data_ptr() if bacc is not None else None
+    _lib.check(lib.esrp_conv3x3_wgrad(arr, len(units), n, h, w, splits, _stream_ptr()), "esrp_conv3x3_wgrad")
+
+
+def wgrad_scatter(entries: Sequence[dict]) -> None:
+    lib = _lib.load()
+    arr = (_lib.ScatterEntry * len(entries))()
+    for i, e in enumerate(entries):
+        arr[i].acc = e["acc"].data_ptr() + 4 * e.get("acc_off", 0)
+        arr[i].dst = e["dst"].data_ptr()
+        arr[i].dst_off = e.get("dst_off", 0)
+        arr[i].dst_index = -1
+        for k in ("kind", "col0", "ncols", "nci", "co0", "ci0", "w_i"):
+            setattr(arr[i], k, e.get(k, 0))
+        arr[i].scale = e.get("scale", 1.0)
+    _lib.check(lib.esrp_wgrad_scatter(arr, len(entries), _stream_ptr()), "esrp_wgrad_scatter")
+
+
+def conv1x1_bwd(x: torch.Tensor, dx2: torch.Tensor, d_c0: int, u: torch.Tensor, g: torch.Tensor,
+                extra: Optional[torch.Tensor] = None, du_acc: Optional[torch.Tensor] = None) -> None:
+    lib = _lib.load()
+    nf = g.shape[-1]
+    npx = g.numel() // nf
+    _lib.check(lib.esrp_conv1x1_bwd(nf, x.data_ptr(), x.shape[-1], dx2.data_ptr(), dx2.shape[-1], d_c0, u.data_ptr(),
+                                    g.data_ptr(), extra.data_ptr() if extra is not None else None,
+                                    du_acc.data_ptr() if du_acc is not None else None, npx, _stream_ptr()),
+               "esrp_conv1x1_bwd")
+
+
+def upsample2x_bwd(dup: torch.Tensor, mask: Optional[torch.Tensor] = None, mask_c0: int = 0, want_f32: bool = False):
+    lib = _lib.load()
+    n, h2, w2, c = dup.shape
+    h, w = h2 // 2, w2 // 2
+    out_b = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dup.device)
+    out_f = torch.empty((n, h, w, c), dtype=torch.float32, device=dup.device) if want_f32 else None
+    _lib.check(lib.esrp_upsample2x_bwd_nhwc_bf16(dup.data_ptr(), n, h, w, c, mask.data_ptr() if mask is not None else None,
+                                                 mask.shape[3] * 16 if mask is not None else 0, mask_c0, out_b.data_ptr(),
+                                                 out_f.data_ptr() if out_f is not None else None, _stream_ptr()),
+               "esrp_upsample2x_bwd_nhwc_bf16")
+    return out_b, out_f

@@ -110,7 +110,7 @@ __device__ __forceinline__ void issue_taps(uint32_t dA, uint32_t dB, uint32_t id
   }
 }
 
-template <int KC, int BN, bool AUX>
+template <int KC, int BN, bool AUX, bool EXT>
 __global__ void __launch_bounds__(kRowThreads, 1)
 conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                    const __grid_constant__ ConvKParams p) {
@@ -397,6 +397,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
             v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b4.z;
             v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b4.w;
           }
+          if constexpr (EXT) ext_mask_store<GC>(p, pix, ch0, v);
           if (p.act) {
 #pragma unroll
             for (int i = 0; i < GC; ++i) v[i] = fmaxf(v[i], 0.2f * v[i]);  // LeakyReLU(0.2)
@@ -414,6 +415,14 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
             for (int i = 0; i < GC; ++i) v[i] = fmaf(p.s1, r1v[i], v[i]);
             if (g + 1 < ROUNDS) load_residual<GC>(p.r1, p.r1_is_f32, pix * p.r1_ctotal + p.r1_c0 + ch0 + GC, r1v);
           }
+          if constexpr (EXT) {
+            if (p.r2 && p.r2_pre) {
+#pragma unroll
+              for (int i = 0; i < GC; ++i) v[i] += r2v[i];
+              if (g + 1 < ROUNDS) load_residual<GC>(p.r2, p.r2_is_f32, pix * p.r2_ctotal + p.r2_c0 + ch0 + GC, r2v);
+            }
+            ext_pre_and_mask<GC>(p, pix, ch0, v);
+          }
           if (p.noise) {
 #pragma unroll 1
             for (int i = 0; i < GC; i += 4) {
@@ -428,7 +437,10 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
               }
             }
           }
-          if (p.r2) {
+          if (EXT && p.r2_pre) {
+#pragma unroll
+            for (int i = 0; i < GC; ++i) v[i] *= p.s2;
+          } else if (p.r2) {
 #pragma unroll
             for (int i = 0; i < GC; ++i) v[i] = fmaf(p.s2, v[i], r2v[i]);
             if (g + 1 < ROUNDS) load_residual<GC>(p.r2, p.r2_is_f32, pix * p.r2_ctotal + p.r2_c0 + ch0 + GC, r2v);

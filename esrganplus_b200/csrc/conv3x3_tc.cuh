@@ -117,7 +117,54 @@ __device__ __forceinline__ void tmem_ld_group(uint32_t taddr, uint32_t (&v)[GC])
   }
 }
 
-template <int KC, int BN>
+
+// ---- training extensions of the fused tail (EXT kernels; see include/esrp.h) ----
+// Forward: save the LeakyReLU derivative selector, one bit per activation (v = acc + bias, pre-activation).
+template <int GC>
+__device__ __forceinline__ void ext_mask_store(const ConvKParams& p, size_t pix, int ch0, const float (&v)[GC]) {
+  if (p.mask_out == nullptr) return;
+  unsigned short* mp = p.mask_out + ((pix * static_cast<size_t>(p.mo_ctotal) + p.mo_c0 + ch0) >> 4);
+#pragma unroll
+  for (int j = 0; j < GC / 16; ++j) {
+    uint32_t bits = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) bits |= (v[16 * j + i] > 0.f ? 1u : 0u) << i;
+    mp[j] = static_cast<unsigned short>(bits);
+  }
+}
+// Backward: copies of the full gradient, then the LeakyReLU derivative from the saved bits.
+template <int GC>
+__device__ __forceinline__ void ext_pre_and_mask(const ConvKParams& p, size_t pix, int ch0, float (&v)[GC]) {
+  if (p.pre_bf16) {
+    uint4* op = reinterpret_cast<uint4*>(p.pre_bf16 + pix * p.pb_ctotal + p.pb_c0 + ch0);
+#pragma unroll
+    for (int i = 0; i < GC / 8; ++i) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+        pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
+      }
+      op[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+  if (p.pre_f32) {
+    float4* op = reinterpret_cast<float4*>(p.pre_f32 + pix * p.pf_ctotal + p.pf_c0 + ch0);
+#pragma unroll
+    for (int i = 0; i < GC / 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
+  if (p.mask_in) {
+    const unsigned short* mp = p.mask_in + ((pix * static_cast<size_t>(p.mi_ctotal) + p.mi_c0 + ch0) >> 4);
+#pragma unroll
+    for (int j = 0; j < GC / 16; ++j) {
+      const uint32_t bits = mp[j];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[16 * j + i] *= ((bits >> i) & 1u) ? 1.0f : 0.2f;
+    }
+  }
+}
+
+template <int KC, int BN, bool EXT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                   const __grid_constant__ ConvKParams p) {
@@ -349,6 +396,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
           const int ch0 = g * GC;
 #pragma unroll
           for (int i = 0; i < GC; ++i) v[i] += bias_s[ch0 + i];
+          if constexpr (EXT) ext_mask_store<GC>(p, pix, ch0, v);
           if (p.act) {
 #pragma unroll
             for (int i = 0; i < GC; ++i) v[i] = lrelu02(v[i]);
@@ -365,6 +413,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
 #pragma unroll
             for (int i = 0; i < GC; ++i) v[i] = fmaf(p.s1, r1v[i], v[i]);
           }
+          if constexpr (EXT) {
+            if (p.r2 && p.r2_pre) {
+#pragma unroll
+              for (int i = 0; i < GC; ++i) v[i] += r2v[i];
+            }
+            ext_pre_and_mask<GC>(p, pix, ch0, v);
+          }
           if (p.noise) {
             // y = t + N(0,1) * sigma * t  (block.py:117-121); one Philox counter per 4 channels of
             // element index e = pixel * noise_ctotal + noise_c0 + channel.
@@ -377,7 +432,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
               for (int j = 0; j < 4; ++j) v[i + j] = fmaf(z[j] * p.sigma, v[i + j], v[i + j]);
             }
           }
-          if (p.r2) {
+          if (EXT && p.r2_pre) {
+#pragma unroll
+            for (int i = 0; i < GC; ++i) v[i] *= p.s2;
+          } else if (p.r2) {
 #pragma unroll
             for (int i = 0; i < GC; ++i) v[i] = fmaf(p.s2, v[i], r2v[i]);
           }

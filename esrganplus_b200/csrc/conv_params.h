@@ -45,6 +45,16 @@ struct ConvKParams {
   float* out_f32;
   int of_ctotal, of_c0;
   float* out_nchw;
+  // training extensions (kernels instantiated with EXT = true only)
+  unsigned short* mask_out;
+  int mo_ctotal, mo_c0;
+  const unsigned short* mask_in;
+  int mi_ctotal, mi_c0;
+  int r2_pre;
+  __nv_bfloat16* pre_bf16;
+  int pb_ctotal, pb_c0;
+  float* pre_f32;
+  int pf_ctotal, pf_c0;
   int dbg;           // timing experiments only (ESRP_DBG_*): results are wrong when non-zero
   long long* trace;  // optional [3][1024] clock64 timeline of CTA 0 (see trace_ev)
 };

@@ -11,8 +11,7 @@
 #include <mutex>
 
 #include "../../include/esrp.h"
-#include "conv3x3_row.cuh"
-#include "conv3x3_tc.cuh"  // kSmemFixed, kMaxStages, kernel template
+#include "esrp_philox.cuh"
 #include "esrp_host.h"
 
 namespace esrp {
@@ -74,7 +73,6 @@ int make_nhwc_tmap(CUtensorMap* tm, const void* ptr, int n, int h, int w, int c_
 // ------------------------------------------------------------------------------------------------
 // conv launch
 // ------------------------------------------------------------------------------------------------
-constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
 
 static int g_sm_count = 0;
 int sm_count() {
@@ -88,188 +86,7 @@ int sm_count() {
   return g_sm_count;
 }
 
-// descriptor fields that map 1:1 onto kernel parameters (both kernels)
-static void copy_common(const esrp_conv3x3_t& d, ConvKParams* pp) {
-  ConvKParams& p = *pp;
-  p.num_chunks = d.num_chunks;
-  for (int i = 0; i < d.num_chunks; ++i) {
-    p.chunk_src[i] = d.chunk_src[i];
-    p.chunk_c0[i] = d.chunk_c0[i];
-  }
-  p.aux_chunks = d.aux_chunks;
-  p.cout = d.cout;
-  p.w_packed = static_cast<const uint8_t*>(d.w_packed);
-  p.bias = d.bias;
-  p.act = d.act; p.s0 = d.s0;
-  p.r1 = d.r1; p.r1_is_f32 = d.r1_is_f32; p.r1_ctotal = d.r1_ctotal; p.r1_c0 = d.r1_c0; p.s1 = d.s1;
-  p.r2 = d.r2; p.r2_is_f32 = d.r2_is_f32; p.r2_ctotal = d.r2_ctotal; p.r2_c0 = d.r2_c0; p.s2 = d.s2;
-  p.noise = d.noise; p.noise_ctotal = d.noise_ctotal; p.noise_c0 = d.noise_c0;
-  p.sigma = d.sigma; p.seed = d.seed; p.offset = d.offset;
-  p.out_bf16 = static_cast<__nv_bfloat16*>(d.out_bf16); p.ob_ctotal = d.ob_ctotal; p.ob_c0 = d.ob_c0;
-  p.out_f32 = static_cast<float*>(d.out_f32); p.of_ctotal = d.of_ctotal; p.of_c0 = d.of_c0;
-  p.out_nchw = d.out_nchw;
-  p.trace = static_cast<long long*>(d.trace);
-  p.dbg = d.variant & 0x1F00;
-}
-
-// ky-stacked row-streaming kernel (conv3x3_row.cuh)
-template <int KC, int BN, bool AUX>
-static int plan_row_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
-  constexpr int RB = KC * 2;
-  ConvKParams& p = out->params;
-  memset(&p, 0, sizeof(p));
-  p.n = d.n; p.h = d.h; p.w = d.w;
-  const bool has_aux = d.aux_chunks > 0;
-  const int nb_rows = (has_aux ? 4 : 3) * BN;
-  const int w_chunk_bytes = 3 * nb_rows * RB;
-  const int w_all = d.num_chunks * w_chunk_bytes;
-  p.nt = nb_rows;
-  const int nblk = (has_aux || BN == 64) ? 8 : 16;  // TMEM ring of output-row blocks (conv3x3_row.cuh)
-  if (has_aux && BN == 64) return set_error("conv3x3(row): bn=64 cannot carry the conv1x1 (TMEM)");
-  p.mt = nblk;
-  p.cw = kRowTile; p.cw_log2 = 7; p.rm = 1;
-  p.x_tiles = (d.w + kRowTile - 1) / kRowTile;
-  p.x_step = kRowTile;
-  p.units_per_col = d.h;
-  p.units_total = static_cast<long long>(d.n) * p.x_tiles * d.h;
-  if (p.units_total > 0x7fffffffLL) return set_error("conv3x3: problem too large (%lld rows)", p.units_total);
-  p.a_box_bytes = (kRowTile + 2) * RB;
-  p.a_stage_bytes = (p.a_box_bytes + 1023) / 1024 * 1024;
-  // row-buffer ring: D >= 2 buffers of num_chunks tiles each (the producer learns that a buffer is free
-  // from the block barrier of the output row its input completed, see conv3x3_row.cuh)
-  const int avail = kMaxSmem - kSmemFixed - 1024;
-  const int row_bytes = p.a_stage_bytes * d.num_chunks;
-  int nbuf = w_all <= avail ? (avail - w_all) / row_bytes : 0;
-  if (nbuf > nblk - 2) nbuf = nblk - 2;  // the producer must not be lapped on a block barrier
-  if (nbuf > kMaxStages) nbuf = kMaxStages;
-  const int force = d.variant & 15;
-  if (force && force < nbuf) nbuf = force;
-  if (nbuf < 2)
-    return set_error("conv3x3(row): weights + 2 row buffers do not fit in shared memory (KC=%d BN=%d chunks=%d); split K", KC, BN, d.num_chunks);
-  p.w_resident = 1;
-  p.stages = nbuf;
-  p.tmem_cols = 512;
-  out->smem = kSmemFixed + 1024 + w_all + p.stages * row_bytes;
-  copy_common(d, &p);
-  if (make_nhwc_tmap(&out->tm0, d.src[0], d.n, d.h, d.w, d.src_ctotal[0], KC, kRowTile + 2, 1)) return 1;
-  if (d.src[1]) {
-    if (make_nhwc_tmap(&out->tm1, d.src[1], d.n, d.h, d.w, d.src_ctotal[1], KC, kRowTile + 2, 1)) return 1;
-  } else {
-    out->tm1 = out->tm0;
-  }
-  auto kern = conv3x3_row_kernel<KC, BN, AUX>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ESRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    attr_set = true;
-  }
-  out->kernel = reinterpret_cast<const void*>(kern);
-  out->threads = kRowThreads;
-  const int sms = sm_count();
-  if (sms <= 0) return set_error("conv3x3: no CUDA device");
-  out->grid = p.units_total < sms ? static_cast<int>(p.units_total) : sms;
-  return 0;
-}
-
-template <int KC, int BN>
-static int plan_conv_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
-  constexpr int RB = KC * 2;
-  ConvKParams& p = out->params;
-  memset(&p, 0, sizeof(p));
-  p.n = d.n; p.h = d.h; p.w = d.w;
-  const bool has_aux = d.aux_chunks > 0;
-  const int nb_rows = (has_aux ? 4 : 3) * BN;
-  const int w_chunk_bytes = 3 * nb_rows * RB;
-  const int w_all = d.num_chunks * w_chunk_bytes;
-  p.nt = nb_rows;
-
-  // M-tile width: the smallest of 16/32/64/128 columns covering the image, else 128 with x-halo blocks
-  int cwl = 4;
-  while (cwl < 7 && (1 << cwl) < d.w) ++cwl;
-  const int force_cwl = (d.variant >> 4) & 15;
-  if (force_cwl) {
-    if (force_cwl < 4 || force_cwl > 7) return set_error("conv3x3: variant forces cw_log2=%d (4..7)", force_cwl);
-    cwl = force_cwl;
-  }
-  p.cw_log2 = cwl;
-  p.cw = 1 << cwl;
-  p.rm = 128 >> cwl;
-  if (d.w <= p.cw) {
-    p.x_tiles = 1;
-    p.x_step = p.cw;
-  } else {
-    p.x_step = p.cw - 2;
-    p.x_tiles = (d.w - 1 + p.x_step - 1) / p.x_step;
-  }
-  p.units_per_col = (d.h + p.rm - 1) / p.rm;
-  p.units_total = static_cast<long long>(d.n) * p.x_tiles * p.units_per_col;
-  if (p.units_total > 0x7fffffffLL) return set_error("conv3x3: problem too large (%lld M-tiles)", p.units_total);
-
-  // accumulator slots per CTA tile: TMEM (mt * nt <= 512) and shared memory (>= 2 stages) permitting
-  const int sms = sm_count();
-  if (sms <= 0) return set_error("conv3x3: no CUDA device");
-  const long long per_cta = (p.units_total + sms - 1) / sms;
-  int mt = 512 / p.nt;
-  if (mt > ESRP_MAX_MT) mt = ESRP_MAX_MT;
-  if (mt > per_cta) mt = static_cast<int>(per_cta);
-  if (mt > p.units_per_col) mt = p.units_per_col;
-  const int force_mt = d.variant & 15;
-  if (force_mt) {
-    if (force_mt > ESRP_MAX_MT || force_mt * p.nt > 512) return set_error("conv3x3: variant forces mt=%d (nt=%d)", force_mt, p.nt);
-    mt = force_mt;
-  }
-  const int avail = kMaxSmem - kSmemFixed - 1024;  // 1 KB alignment slack
-  auto a_stage = [&](int m) { return ((m * p.rm + 2) * p.cw * RB + 1023) / 1024 * 1024; };
-  // largest tile with resident weights and >= 2 stages; else stream the weights with the chunks
-  int best_mt = 0, best_res = 0, best_s = 0;
-  for (int pass = 0; pass < 2 && !best_mt; ++pass) {
-    for (int m = mt; m >= 1; --m) {
-      const int s_res = w_all <= avail ? (avail - w_all) / a_stage(m) : 0;
-      const int s_str = avail / (a_stage(m) + w_chunk_bytes);
-      if (pass == 0 && s_res >= 2) { best_mt = m; best_res = 1; best_s = s_res; break; }
-      if (pass == 1 && s_str >= 2) { best_mt = m; best_res = 0; best_s = s_str; break; }
-      if (force_mt) break;
-    }
-  }
-  if (!best_mt) {
-    const int s_res = (avail - w_all) / a_stage(mt), s_str = avail / (a_stage(mt) + w_chunk_bytes);
-    if (w_all <= avail && s_res >= 1) { best_mt = mt; best_res = 1; best_s = s_res; }
-    else if (s_str >= 1) { best_mt = mt; best_res = 0; best_s = s_str; }
-    else return set_error("conv3x3: tile does not fit in shared memory (KC=%d BN=%d chunks=%d)", KC, BN, d.num_chunks);
-  }
-  p.mt = best_mt;
-  p.w_resident = best_res;
-  p.stages = best_s > kMaxStages ? kMaxStages : best_s;
-  p.a_box_bytes = (p.mt * p.rm + 2) * p.cw * RB;
-  p.a_stage_bytes = a_stage(p.mt);
-  uint32_t cols = 32;
-  while (cols < static_cast<uint32_t>(p.mt * p.nt)) cols <<= 1;
-  p.tmem_cols = cols;
-  out->smem = kSmemFixed + 1024 + (p.w_resident ? w_all : 0) +
-              p.stages * (p.a_stage_bytes + (p.w_resident ? 0 : w_chunk_bytes));
-
-  copy_common(d, &p);
-
-  const int box_rows = p.mt * p.rm + 2;
-  if (make_nhwc_tmap(&out->tm0, d.src[0], d.n, d.h, d.w, d.src_ctotal[0], KC, p.cw, box_rows)) return 1;
-  if (d.src[1]) {
-    if (make_nhwc_tmap(&out->tm1, d.src[1], d.n, d.h, d.w, d.src_ctotal[1], KC, p.cw, box_rows)) return 1;
-  } else {
-    out->tm1 = out->tm0;
-  }
-
-  auto kern = conv3x3_tc_kernel<KC, BN>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
-    ESRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    attr_set = true;
-  }
-  out->kernel = reinterpret_cast<const void*>(kern);
-  out->threads = kConvThreads;
-  out->grid = p.units_total < sms ? static_cast<int>(p.units_total) : sms;
-  return 0;
-}
-
+// kernel instantiations live in esrp_conv_{row,tile}{,_ext}.cu (one translation unit per family so they build in parallel)
 int run_conv(const ConvLaunch& L, cudaStream_t stream) {
   if (L.grid < 1) return 0;
   void* args[3] = {const_cast<CUtensorMap*>(&L.tm0), const_cast<CUtensorMap*>(&L.tm1),
@@ -313,32 +130,17 @@ int plan_conv(const esrp_conv3x3_t& d, ConvLaunch* out) {
   if (d.r2 && ((d.r2_ctotal % 8) || (d.r2_c0 % 8))) return set_error("conv3x3: r2 channel alignment");
   if ((d.out_bf16 || d.out_f32 || d.r1 || d.r2) && (d.cout % 16)) return set_error("conv3x3: NHWC outputs/residuals need cout %% 16 == 0");
   if (d.noise && ((d.noise_ctotal % 4) || (d.noise_c0 % 4) || d.noise_ctotal < d.cout)) return set_error("conv3x3: noise_ctotal/noise_c0 must be multiples of 4 and cover cout");
-  if (d.w_layout == ESRP_LAYOUT_ROW) {
-    const bool aux = d.aux_chunks > 0;
-    if (d.kc == 64 && d.bn == 16) return aux ? plan_row_t<64, 16, true>(d, out) : plan_row_t<64, 16, false>(d, out);
-    if (d.kc == 64 && d.bn == 32) return aux ? plan_row_t<64, 32, true>(d, out) : plan_row_t<64, 32, false>(d, out);
-    if (d.kc == 32 && d.bn == 16) return aux ? plan_row_t<32, 16, true>(d, out) : plan_row_t<32, 16, false>(d, out);
-    if (d.kc == 32 && d.bn == 32) return aux ? plan_row_t<32, 32, true>(d, out) : plan_row_t<32, 32, false>(d, out);
-    if (d.kc == 64 && d.bn == 64) return plan_row_t<64, 64, false>(d, out);
-    if (d.kc == 32 && d.bn == 64) return plan_row_t<32, 64, false>(d, out);
-    return set_error("conv3x3(row): unsupported kc=%d bn=%d (kc in {32,64}, bn in {16,32,64})", d.kc, d.bn);
-  }
+  const bool ext = d.mask_out || d.mask_in || d.pre_bf16 || d.pre_f32 || d.r2_pre;
+  if (d.mask_out && ((d.mask_out_ctotal % 16) || (d.mask_out_c0 % 16) || (d.cout % 16))) return set_error("conv3x3: mask_out needs 16-bit aligned channel ranges");
+  if (d.mask_in && ((d.mask_in_ctotal % 16) || (d.mask_in_c0 % 16) || (d.cout % 16))) return set_error("conv3x3: mask_in needs 16-bit aligned channel ranges");
+  if (d.pre_bf16 && ((d.pb_ctotal % 8) || (d.pb_c0 % 8) || (d.cout % 16))) return set_error("conv3x3: pre_bf16 channel alignment");
+  if (d.pre_f32 && ((d.pf_ctotal % 4) || (d.pf_c0 % 4) || (d.cout % 16))) return set_error("conv3x3: pre_f32 channel alignment");
+  if (d.r2_pre && !d.r2) return set_error("conv3x3: r2_pre without r2");
+  if (d.w_layout == ESRP_LAYOUT_ROW) return ext ? plan_row_ext(d, out) : plan_row_base(d, out);
   if (d.w_layout != ESRP_LAYOUT_TILE) return set_error("conv3x3: unknown w_layout=%d", d.w_layout);
-  if (d.kc == 64) {
-    switch (d.bn) {
-      case 16: return plan_conv_t<64, 16>(d, out);
-      case 32: return plan_conv_t<64, 32>(d, out);
-      case 64: return plan_conv_t<64, 64>(d, out);
-    }
-  } else if (d.kc == 32) {
-    switch (d.bn) {
-      case 16: return plan_conv_t<32, 16>(d, out);
-      case 32: return plan_conv_t<32, 32>(d, out);
-      case 64: return plan_conv_t<32, 64>(d, out);
-    }
-  }
-  return set_error("conv3x3: unsupported kc=%d bn=%d (kc in {32,64}, bn in {16,32,64})", d.kc, d.bn);
+  return ext ? plan_tile_ext(d, out) : plan_tile_base(d, out);
 }
+
 
 // ------------------------------------------------------------------------------------------------
 // weight repack: [w_o, w_i, 3, 3] fp32 -> [chunk][ky][row][kc] bf16, rows pre-swizzled for UMMA/TMA

@@ -26,6 +26,13 @@ struct ConvLaunch {
   int smem = 0;
 };
 int plan_conv(const esrp_conv3x3_t& d, ConvLaunch* out);
+// per-family planners (esrp_conv_{row,tile}{,_ext}.cu); *_ext carry the training extensions of the fused tail
+int plan_row_base(const esrp_conv3x3_t& d, ConvLaunch* out);
+int plan_row_ext(const esrp_conv3x3_t& d, ConvLaunch* out);
+int plan_tile_base(const esrp_conv3x3_t& d, ConvLaunch* out);
+int plan_tile_ext(const esrp_conv3x3_t& d, ConvLaunch* out);
+void copy_common(const esrp_conv3x3_t& d, ConvKParams* pp);
+constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
 int run_conv(const ConvLaunch& L, cudaStream_t stream);
 
 #define ESRP_CUDA_OK(expr)                                                              \

@@ -1,0 +1,89 @@
+// plan_row.inl — launch planning + instantiations of conv3x3_row_kernel for one value of ESRP_EXT
+// (included by esrp_conv_row.cu with ESRP_EXT = false and esrp_conv_row_ext.cu with ESRP_EXT = true).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstring>
+
+#include "../../include/esrp.h"
+#include "conv3x3_row.cuh"
+#include "esrp_host.h"
+
+namespace esrp {
+
+// ky-stacked row-streaming kernel (conv3x3_row.cuh)
+template <int KC, int BN, bool AUX, bool EXT>
+static int plan_row_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
+  constexpr int RB = KC * 2;
+  ConvKParams& p = out->params;
+  memset(&p, 0, sizeof(p));
+  p.n = d.n; p.h = d.h; p.w = d.w;
+  const bool has_aux = d.aux_chunks > 0;
+  const int nb_rows = (has_aux ? 4 : 3) * BN;
+  const int w_chunk_bytes = 3 * nb_rows * RB;
+  const int w_all = d.num_chunks * w_chunk_bytes;
+  p.nt = nb_rows;
+  const int nblk = (has_aux || BN == 64) ? 8 : 16;  // TMEM ring of output-row blocks (conv3x3_row.cuh)
+  if (has_aux && BN == 64) return set_error("conv3x3(row): bn=64 cannot carry the conv1x1 (TMEM)");
+  p.mt = nblk;
+  p.cw = kRowTile; p.cw_log2 = 7; p.rm = 1;
+  p.x_tiles = (d.w + kRowTile - 1) / kRowTile;
+  p.x_step = kRowTile;
+  p.units_per_col = d.h;
+  p.units_total = static_cast<long long>(d.n) * p.x_tiles * d.h;
+  if (p.units_total > 0x7fffffffLL) return set_error("conv3x3: problem too large (%lld rows)", p.units_total);
+  p.a_box_bytes = (kRowTile + 2) * RB;
+  p.a_stage_bytes = (p.a_box_bytes + 1023) / 1024 * 1024;
+  // row-buffer ring: D >= 2 buffers of num_chunks tiles each (the producer learns that a buffer is free
+  // from the block barrier of the output row its input completed, see conv3x3_row.cuh)
+  const int avail = kMaxSmem - kSmemFixed - 1024;
+  const int row_bytes = p.a_stage_bytes * d.num_chunks;
+  int nbuf = w_all <= avail ? (avail - w_all) / row_bytes : 0;
+  if (nbuf > nblk - 2) nbuf = nblk - 2;  // the producer must not be lapped on a block barrier
+  if (nbuf > kMaxStages) nbuf = kMaxStages;
+  const int force = d.variant & 15;
+  if (force && force < nbuf) nbuf = force;
+  if (nbuf < 2)
+    return set_error("conv3x3(row): weights + 2 row buffers do not fit in shared memory (KC=%d BN=%d chunks=%d); split K", KC, BN, d.num_chunks);
+  p.w_resident = 1;
+  p.stages = nbuf;
+  p.tmem_cols = 512;
+  out->smem = kSmemFixed + 1024 + w_all + p.stages * row_bytes;
+  copy_common(d, &p);
+  if (make_nhwc_tmap(&out->tm0, d.src[0], d.n, d.h, d.w, d.src_ctotal[0], KC, kRowTile + 2, 1)) return 1;
+  if (d.src[1]) {
+    if (make_nhwc_tmap(&out->tm1, d.src[1], d.n, d.h, d.w, d.src_ctotal[1], KC, kRowTile + 2, 1)) return 1;
+  } else {
+    out->tm1 = out->tm0;
+  }
+  auto kern = conv3x3_row_kernel<KC, BN, AUX, EXT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ESRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    attr_set = true;
+  }
+  out->kernel = reinterpret_cast<const void*>(kern);
+  out->threads = kRowThreads;
+  const int sms = sm_count();
+  if (sms <= 0) return set_error("conv3x3: no CUDA device");
+  out->grid = p.units_total < sms ? static_cast<int>(p.units_total) : sms;
+  return 0;
+}
+
+
+int ESRP_PLAN_ROW_NAME(const esrp_conv3x3_t& d, ConvLaunch* out) {
+  constexpr bool X = ESRP_EXT;
+  const bool aux = d.aux_chunks > 0;
+  if constexpr (!X) {
+    if (d.kc == 64 && d.bn == 16) return aux ? plan_row_t<64, 16, true, false>(d, out) : plan_row_t<64, 16, false, false>(d, out);
+    if (d.kc == 32 && d.bn == 16) return aux ? plan_row_t<32, 16, true, false>(d, out) : plan_row_t<32, 16, false, false>(d, out);
+  }
+  if (d.kc == 64 && d.bn == 32) return aux ? plan_row_t<64, 32, true, X>(d, out) : plan_row_t<64, 32, false, X>(d, out);
+  if (d.kc == 32 && d.bn == 32) return aux ? plan_row_t<32, 32, true, X>(d, out) : plan_row_t<32, 32, false, X>(d, out);
+  if (d.kc == 64 && d.bn == 64) return plan_row_t<64, 64, false, X>(d, out);
+  if (d.kc == 32 && d.bn == 64) return plan_row_t<32, 64, false, X>(d, out);
+  return set_error("conv3x3(row%s): unsupported kc=%d bn=%d (kc in {32,64}, bn in {%s32,64})", X ? ", training extensions" : "", d.kc, d.bn, X ? "" : "16,");
+}
+
+}  // namespace esrp

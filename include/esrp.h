@@ -58,6 +58,16 @@ extern "C" {
  *   v    = v * (1 + sigma * N(0,1))           if noise                            (:117-121)
  *   v    = s2 * v + r2                        if r2                               (:291)
  *   out_* <- v
+ *
+ * Training extensions (the autograd backward of the same lines, SRRaGAN_model.py:140,167):
+ *   mask_out : bit (mask_out_c0 + ch) of pixel's mask word row <- (acc + bias > 0), the LeakyReLU
+ *              derivative selector saved by the forward pass (1 bit per activation);
+ *   r2_pre   : r2 is added BEFORE the pre_* stores (v += r2) and s2 becomes a plain final scale;
+ *   pre_bf16 / pre_f32 : copies of v taken before mask_in / noise / s2 (the gradient of a tensor
+ *              that is both an operand of a later launch and the input of an activation);
+ *   mask_in  : v *= bit ? 1 : 0.2  (LeakyReLU backward) — applied after the pre_* stores.
+ * The data-gradient of a conv is this same operator over weights packed by
+ * esrp_pack_dgrad_weights; the gradient of a dense block is again a dense block.
  */
 typedef struct esrp_conv3x3 {
   int32_t n, h, w;              /* batch, height, width (output == input spatial size)       */
@@ -92,6 +102,16 @@ typedef struct esrp_conv3x3 {
   float* out_nchw;              /* NCHW fp32 [n,cout,h,w], or NULL                           */
   int32_t variant;              /* ESRP_VARIANT_* bits                                       */
   void* trace;                  /* NULL, or device int64[3*1024]: clock64 timeline of CTA 0  */
+  /* ---- training extensions (all optional; zero = off) ---- */
+  void* mask_out;               /* uint16 words, [n*h*w][mask_out_ctotal/16]; bit = pre-act > 0 */
+  int32_t mask_out_ctotal, mask_out_c0; /* bits per pixel / first bit (multiples of 16)       */
+  const void* mask_in;          /* same format; v *= bit ? 1 : 0.2                            */
+  int32_t mask_in_ctotal, mask_in_c0;
+  int32_t r2_pre;               /* 1: v += r2 before the pre_* stores; s2 scales at the end   */
+  void* pre_bf16;               /* NHWC bf16 copy of v before mask_in/noise/s2, or NULL       */
+  int32_t pb_ctotal, pb_c0;
+  void* pre_f32;                /* NHWC fp32 copy of v before mask_in/noise/s2, or NULL       */
+  int32_t pf_ctotal, pf_c0;
 } esrp_conv3x3_t;
 
 const char* esrp_last_error(void);
@@ -154,6 +174,62 @@ int esrp_bn_apply_nhwc(const float* x, int32_t n, int32_t h, int32_t w, int32_t 
 /* nn.Linear (+ optional LeakyReLU 0.2): y[b,o] = sum_k x[b,k] w[o,k] + bias[o]  (architecture.py:122-123). */
 int esrp_linear_f32(const float* x, const float* w, const float* bias, float* y, int32_t b, int32_t k, int32_t o,
                     int32_t act, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Backward pass (autograd of block.py:260-268 / architecture.py:47-78 as driven by
+ * SRRaGAN_model.py:140,167).  Data gradients run on esrp_conv3x3_nhwc over weights packed here;
+ * weight gradients are accumulated per "unit" (32 input channels x 64 output-gradient channels x 9
+ * taps) and scattered into the reference's OIHW fp32 layout.
+ * ------------------------------------------------------------------------------------------- */
+/* One 32-channel group of the K dimension of a data-gradient conv: K channel k of the group is the
+ * gradient of output channel co0 + k of the source conv w [w_o, w_i, 3, 3] (fp32, device); w == NULL
+ * packs zeros (a group that is not an operand of this slice). */
+typedef struct esrp_dgrad_group {
+  const float* w;
+  int32_t w_o, w_i;
+  int32_t co0;
+  float scale;
+} esrp_dgrad_group_t;
+/* Packs rows [row0, row0+rows) (= INPUT channels of the source convs = output channels of the data
+ * gradient) over num_groups K groups (chunks of kc = 32 or 64 channels: ceil(num_groups*32/kc) chunks,
+ * size esrp_packed_conv3x3_bytes(chunks, kc, bn, 0)); taps are flipped (conv_transpose). */
+int esrp_pack_dgrad_weights(const esrp_dgrad_group_t* groups_host, int32_t num_groups, int32_t layout,
+                            int32_t row0, int32_t rows, int32_t kc, int32_t bn, void* out, void* stream);
+
+#define ESRP_WGRAD_MAX_UNITS 16
+/* acc[tap = ky*3+kx][c < 64][i < 32] += sum_px dy[px][dy_c0 + c] * x[px + (ky-1, kx-1)][x_c0 + i]
+ * (zero padding; dy channels beyond dy_ctotal read as zero); bias_acc[c] += sum_px dy[px][dy_c0 + c]. */
+typedef struct esrp_wgrad_unit {
+  const void* x;                /* NHWC bf16 [n,h,w,x_ctotal]  */
+  int32_t x_ctotal, x_c0;
+  const void* dy;               /* NHWC bf16 [n,h,w,dy_ctotal] */
+  int32_t dy_ctotal, dy_c0;
+  float* acc;                   /* fp32 [9][64][32], accumulated atomically (zero it first) */
+  float* bias_acc;              /* fp32 [64] or NULL */
+} esrp_wgrad_unit_t;
+/* All units share the spatial shape; splits = CTAs per unit over the pixel dimension (0 = fill the GPU). */
+int esrp_conv3x3_wgrad(const esrp_wgrad_unit_t* units_host, int32_t num_units, int32_t n, int32_t h, int32_t w,
+                       int32_t splits, void* stream);
+/* kind 0: dst[dst_off + ((co0 + c) * w_i + ci0 + i) * 9 + tap] = scale * acc[tap][col0 + c][i], c < ncols, i < nci
+ * kind 1: dst[dst_off + i] = scale * acc[i], i < ncols.  dst_index is used by the engines only. */
+typedef struct esrp_scatter_entry {
+  const float* acc;
+  float* dst;
+  int64_t dst_off;
+  int32_t dst_index;
+  int32_t kind, col0, ncols, nci, co0, ci0, w_i;
+  float scale;
+} esrp_scatter_entry_t;
+int esrp_wgrad_scatter(const esrp_scatter_entry_t* entries_host, int32_t num, void* stream);
+/* Bias-free 1x1 conv of block.py:244,263, both gradients: g[px][0:nf] (fp32, in place) += u^T dx2[px]
+ * (+ extra[px] if extra != NULL); du_acc[32][nf] (fp32, atomics; NULL to skip) += dx2 (x) x.
+ * x: NHWC bf16 (first nf of x_ctotal channels), dx2: NHWC bf16 32 channels at d_c0, u: fp32 [32][nf]. */
+int esrp_conv1x1_bwd(int32_t nf, const void* x, int32_t x_ctotal, const void* dx2, int32_t d_ctotal, int32_t d_c0,
+                     const float* u, float* g, const float* extra, float* du_acc, int64_t npx, void* stream);
+/* nn.Upsample(x2, nearest) backward: [n,2h,2w,c] bf16 -> 2x2 sums [n,h,w,c] (fp32 out_f32, unmasked) and
+ * bf16 out_bf16 after the optional LeakyReLU mask (bit mask_c0 + ch of the pixel's mask_ctotal bits). */
+int esrp_upsample2x_bwd_nhwc_bf16(const void* dup, int32_t n, int32_t h, int32_t w, int32_t c, const void* mask,
+                                  int32_t mask_ctotal, int32_t mask_c0, void* out_bf16, float* out_f32, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * RRDBNet generator engine: what RRDBNet.forward / RRDB_Net.forward binds to
