@@ -143,6 +143,12 @@ SYMBOLS = {
     "esrp_rrdbnet_num_launches": (C.c_int32, [C.c_void_p]),
     "esrp_rrdbnet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_void_p]),
+    "esrp_rrdbnet_train_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    "esrp_rrdbnet_train_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                             C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_void_p]),
+    "esrp_rrdbnet_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p,
+                                        C.c_void_p]),
+    "esrp_rrdbnet_train_num_launches": (C.c_int32, [C.c_void_p, C.c_int32]),
 }
 
 _lib = None

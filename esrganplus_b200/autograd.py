@@ -1,8 +1,66 @@
-"""Training-mode (autograd) entry of the generator.  Backward kernels land here."""
+"""Training-mode (autograd) entry of the generator: one autograd.Function whose forward/backward are the
+native esrp_rrdbnet_train_forward / esrp_rrdbnet_backward (SRRaGAN_model.py:120,140 drive them through
+``self.netG(self.var_L)`` and ``l_g_total.backward()``).  Gradients land in ``.grad`` of the fp32 OIHW
+Parameters, which is what ``torch.optim.Adam`` (SRRaGAN_model.py:82-89) consumes.
+
+Data parallelism (one process per GPU): when ``torch.distributed`` is initialised and the module was
+marked with ``esrganplus_b200.data_parallel(module)``, the flat gradient buffer the backward fills is
+all-reduced (average) with ONE collective before the per-tensor views are handed to autograd — the only
+exchange step of the path.
+"""
 from __future__ import annotations
 
+from typing import Dict
 
-def generator_apply(module, x, params):
-    raise NotImplementedError(
-        "esrganplus_b200: the generator backward pass (dgrad/wgrad kernels) is not built yet; "
-        "run under torch.no_grad() / with requires_grad=False parameters for inference")
+import torch
+
+
+class _GeneratorFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, eng, noise, seed, x, *params):
+        y, token = eng.train_forward(x, noise, seed)
+        ctx.eng = eng
+        ctx.token = token
+        ctx.module = module
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        needs = list(ctx.needs_input_grad[5:])
+        grads, flat = ctx.eng.backward(dy, ctx.token, needs)
+        group = getattr(ctx.module, "_dp_group", False)
+        if group is not False:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                pg = None if group is True else group
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=pg)
+                flat.mul_(1.0 / dist.get_world_size(pg))
+        return (None, None, None, None, None) + tuple(grads)
+
+
+def generator_apply(module, x: torch.Tensor, params: Dict[str, torch.Tensor]) -> torch.Tensor:
+    if x.requires_grad:
+        raise NotImplementedError(
+            "esrganplus_b200.RRDBNet: the gradient w.r.t. the LR input is not produced (the reference never asks "
+            "for it, SRRaGAN_model.py:103-111); detach the input")
+    eng = module._engine_for(x.device)
+    eng.sync_weights(params)
+    plist = []
+    for k in eng.keys:
+        plist.append(params[k])
+    noise = bool(module.training)
+    return _GeneratorFn.apply(module, eng, noise, module.noise_seed() if noise else 0, x, *plist)
+
+
+def data_parallel(module, process_group=True):
+    """Mark a generator/discriminator for data-parallel training: its backward all-reduces (averages) the
+    flat gradient buffer over `process_group` (True = the default group).  Parameters must start identical
+    on every rank (broadcast them once, e.g. ``broadcast_parameters``)."""
+    object.__setattr__(module, "_dp_group", process_group)
+    return module
+
+
+def broadcast_parameters(module, src: int = 0, process_group=None) -> None:
+    import torch.distributed as dist
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src, group=process_group)

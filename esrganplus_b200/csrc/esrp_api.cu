@@ -135,7 +135,6 @@ int plan_conv(const esrp_conv3x3_t& d, ConvLaunch* out) {
   if (d.mask_in && ((d.mask_in_ctotal % 16) || (d.mask_in_c0 % 16) || (d.cout % 16))) return set_error("conv3x3: mask_in needs 16-bit aligned channel ranges");
   if (d.pre_bf16 && ((d.pb_ctotal % 8) || (d.pb_c0 % 8) || (d.cout % 16))) return set_error("conv3x3: pre_bf16 channel alignment");
   if (d.pre_f32 && ((d.pf_ctotal % 4) || (d.pf_c0 % 4) || (d.cout % 16))) return set_error("conv3x3: pre_f32 channel alignment");
-  if (d.r2_pre && !d.r2) return set_error("conv3x3: r2_pre without r2");
   if (d.w_layout == ESRP_LAYOUT_ROW) return ext ? plan_row_ext(d, out) : plan_row_base(d, out);
   if (d.w_layout != ESRP_LAYOUT_TILE) return set_error("conv3x3: unknown w_layout=%d", d.w_layout);
   return ext ? plan_tile_ext(d, out) : plan_tile_base(d, out);

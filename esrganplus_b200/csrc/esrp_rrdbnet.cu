@@ -33,59 +33,9 @@
 
 #include "../../include/esrp.h"
 #include "esrp_host.h"
+#include "esrp_rrdbnet_int.h"
 
 namespace esrp {
-
-namespace {
-
-struct ConvW {
-  int cin = 0, cout = 0;       // logical channels of the reference tensor [cout, cin, 3, 3]
-  int row0 = 0, rows = 0;      // output-channel slice this launch computes
-  int kc = 0, bn = 0;
-  int num_chunks = 0;
-  int lc0[ESRP_MAX_CHUNKS] = {0};  // logical first input channel per chunk
-  int aux_chunks = 0;              // leading chunks feeding the fused 1x1
-  int w_idx = -1, b_idx = -1, aux_idx = -1;  // indices into the key list
-  size_t w_off = 0, b_off = 0;     // packed device storage (offsets into wbuf)
-  int layout = -1;                 // ESRP_LAYOUT_* currently packed (-1: none)
-};
-
-struct Step {
-  enum Kind { kConv, kPackInput, kUpsample } kind = kConv;
-  ConvLaunch conv;
-  const void* src = nullptr;
-  void* dst = nullptr;
-  int n = 0, h = 0, w = 0, c = 0, c_pad = 0;
-  bool patch_y = false;      // conv writes the caller's output tensor
-  bool is_noise = false;     // conv5 with GaussianNoise (training)
-  int noise_index = 0;
-};
-
-size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-int layout_for_width(int w) { return w > 64 ? ESRP_LAYOUT_ROW : ESRP_LAYOUT_TILE; }
-
-}  // namespace
-
-struct Rrdbnet {
-  int in_nc, out_nc, nf, nb, gc, upscale, n_up;
-  int in_pad;  // input channels padded to 32
-  std::vector<std::string> keys;
-  std::vector<std::vector<int>> shapes;
-  // every logical conv is a list of <= 32-output-channel launches
-  std::vector<ConvW> fea, trunk, up[2], hr0, hr1;
-  std::vector<ConvW> rdb;  // nb*3*per_rdb: conv1..4, then conv5 as nf/32 output-channel slices
-  int per_rdb = 5;
-  uint8_t* wbuf = nullptr;
-  size_t wbytes = 0;
-  bool weights_loaded = false;
-  std::vector<const void*> src_ptrs;  // borrowed fp32 tensors of the last load_weights (for re-layout)
-  // plan cache (single entry: the common case is a fixed shape)
-  int pn = 0, ph = 0, pw = 0, ptraining = -1;
-  void* pws = nullptr;
-  bool g_zeroed = false;
-  std::vector<Step> steps;
-};
 
 namespace {
 
@@ -121,6 +71,8 @@ void define_conv(Rrdbnet* m, std::vector<ConvW>* out, const std::string& key, in
   }
 }
 
+}  // namespace
+
 int pack_one(Rrdbnet* m, ConvW* c, int layout, cudaStream_t s) {
   const void* const* ptrs = m->src_ptrs.data();
   const float* aux = c->aux_idx >= 0 ? static_cast<const float*>(ptrs[c->aux_idx]) : nullptr;
@@ -135,19 +87,22 @@ int pack_one(Rrdbnet* m, ConvW* c, int layout, cudaStream_t s) {
   return 0;
 }
 
-template <class F>
-int for_each_conv(Rrdbnet* m, F&& f) {
-  for (auto& c : m->fea) if (f(&c)) return 1;
-  for (auto& c : m->rdb) if (f(&c)) return 1;
-  for (auto& c : m->trunk) if (f(&c)) return 1;
-  for (int u = 0; u < m->n_up; ++u)
-    for (auto& c : m->up[u]) if (f(&c)) return 1;
-  for (auto& c : m->hr0) if (f(&c)) return 1;
-  for (auto& c : m->hr1) if (f(&c)) return 1;
-  return 0;
+int ensure_layouts(Rrdbnet* m, int w, cudaStream_t s) {
+  auto want = [&](std::vector<ConvW>& cs, int width) -> int {
+    const int lay = layout_for_width(width);
+    for (auto& c : cs)
+      if (c.layout != lay && pack_one(m, &c, lay, s)) return 1;
+    return 0;
+  };
+  if (want(m->fea, w) || want(m->rdb, w) || want(m->trunk, w)) return 1;
+  int ww = w;
+  for (int u = 0; u < m->n_up; ++u) {
+    ww *= 2;
+    if (want(m->up[u], ww)) return 1;
+  }
+  return want(m->hr0, ww) || want(m->hr1, ww);
 }
 
-}  // namespace
 }  // namespace esrp
 
 using namespace esrp;
@@ -206,6 +161,7 @@ int esrp_rrdbnet_create(int32_t in_nc, int32_t out_nc, int32_t nf, int32_t nb, i
 void esrp_rrdbnet_destroy(esrp_rrdbnet_t* h) {
   Rrdbnet* m = reinterpret_cast<Rrdbnet*>(h);
   if (!m) return;
+  destroy_train_state(m);
   if (m->wbuf) cudaFree(m->wbuf);
   delete m;
 }
@@ -239,12 +195,29 @@ int esrp_rrdbnet_load_weights(esrp_rrdbnet_t* h, const void* const* ptrs, int32_
   // keep each conv in the layout its last plan asked for (ROW until a plan says otherwise)
   if (for_each_conv(m, [&](ConvW* c) { return pack_one(m, c, c->layout < 0 ? ESRP_LAYOUT_ROW : c->layout, s); })) return 1;
   m->weights_loaded = true;
+  ++m->weights_version;
   return 0;
 }
 
 }  // extern "C"
 
 namespace esrp {
+
+// Fill the common part of a conv descriptor from packed weights.
+void base_desc(const Rrdbnet* m, const ConvW& c, int n, int h, int w, esrp_conv3x3_t* d) {
+  memset(d, 0, sizeof(*d));
+  d->n = n; d->h = h; d->w = w;
+  d->kc = c.kc;
+  d->num_chunks = c.num_chunks;
+  d->bn = c.bn;
+  d->cout = c.rows;
+  d->w_packed = m->wbuf + c.w_off;
+  d->w_layout = c.layout;
+  d->bias = reinterpret_cast<const float*>(m->wbuf + c.b_off);
+  d->s0 = 1.f; d->s1 = 1.f; d->s2 = 1.f;
+  d->sigma = 0.1f;
+}
+
 namespace {
 
 struct Workspace {
@@ -276,21 +249,6 @@ Workspace layout(const Rrdbnet* m, int n, int h, int w) {
   ws.hr_c = take(px * s * m->nf * 2);
   ws.total = off;
   return ws;
-}
-
-// Fill the common part of a conv descriptor from packed weights.
-void base_desc(const Rrdbnet* m, const ConvW& c, int n, int h, int w, esrp_conv3x3_t* d) {
-  memset(d, 0, sizeof(*d));
-  d->n = n; d->h = h; d->w = w;
-  d->kc = c.kc;
-  d->num_chunks = c.num_chunks;
-  d->bn = c.bn;
-  d->cout = c.rows;
-  d->w_packed = m->wbuf + c.w_off;
-  d->w_layout = c.layout;
-  d->bias = reinterpret_cast<const float*>(m->wbuf + c.b_off);
-  d->s0 = 1.f; d->s1 = 1.f; d->s2 = 1.f;
-  d->sigma = 0.1f;
 }
 
 int build_plan(Rrdbnet* m, int n, int h, int w, uint8_t* wsp, int training, cudaStream_t stream) {
@@ -459,6 +417,8 @@ int esrp_rrdbnet_forward(esrp_rrdbnet_t* h, const float* x, float* y, int32_t n,
   if (workspace_bytes < need) return set_error("rrdbnet_forward: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
   if (reinterpret_cast<uintptr_t>(workspace) % 1024) return set_error("rrdbnet_forward: workspace must be 1024-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // another plan (e.g. the training plan at a different crop size) may have re-laid the weights out
+  if (ensure_layouts(m, w, s)) return 1;
   if (m->pn != n || m->ph != hh || m->pw != w || m->pws != workspace || m->ptraining != (training ? 1 : 0)) {
     if (build_plan(m, n, hh, w, static_cast<uint8_t*>(workspace), training ? 1 : 0, s)) {
       m->pn = 0;

@@ -100,3 +100,96 @@ class GeneratorEngine:
     @property
     def num_launches(self) -> int:
         return self.lib.esrp_rrdbnet_num_launches(self.handle)
+
+    # -- training --------------------------------------------------------------------------------
+    def _check_input(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dim() != 4 or x.dtype != torch.float32 or x.device != self.device:
+            raise RuntimeError(f"RRDBNet forward expects an fp32 NCHW tensor on {self.device}, got {x.dtype} {tuple(x.shape)} on {x.device}")
+        if x.shape[1] != self.cfg[0]:
+            raise RuntimeError(f"RRDBNet forward: expected {self.cfg[0]} input channels, got {x.shape[1]}")
+        return x.contiguous()
+
+    def train_forward(self, x: torch.Tensor, noise: bool, seed: int):
+        """Forward that keeps the activations the backward needs (esrp_rrdbnet_train_forward).  Returns
+        (y, token); the token names this forward's saved state: a later train_forward on the same shape
+        reuses the workspace and invalidates older tokens."""
+        x = self._check_input(x)
+        n, _, h, w = x.shape
+        key = ("train", n, h, w)
+        ws = self._ws.get(key)
+        if ws is None:
+            nbytes = self.lib.esrp_rrdbnet_train_workspace_bytes(self.handle, n, h, w)
+            if nbytes < 0:
+                raise RuntimeError("esrp_rrdbnet_train_workspace_bytes failed")
+            for k in [k for k in self._ws if k[0] == "train"]:
+                del self._ws[k]
+            ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        base = ws.data_ptr()
+        aligned = (base + 1023) // 1024 * 1024
+        y = torch.empty((n, self.out_nc, h * self.upscale, w * self.upscale), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.esrp_rrdbnet_train_forward(self.handle, x.data_ptr(), y.data_ptr(), n, h, w, aligned,
+                                                           ws.numel() - (aligned - base), int(bool(noise)),
+                                                           seed & 0xFFFFFFFFFFFFFFFF,
+                                                           torch.cuda.current_stream(self.device).cuda_stream),
+                       "esrp_rrdbnet_train_forward")
+        self._train_token = getattr(self, "_train_token", 0) + 1
+        self._train_ws = (ws, aligned)
+        return y, self._train_token
+
+    def _grad_layout(self):
+        lay = getattr(self, "_glay", None)
+        if lay is None:
+            import numpy as np
+            dims = (C.c_int32 * 4)()
+            shapes, offs, off = [], [], 0
+            for i in range(len(self.keys)):
+                _lib.check(self.lib.esrp_rrdbnet_tensor_shape(self.handle, i, dims), "esrp_rrdbnet_tensor_shape")
+                shp = tuple(int(d) for d in dims if d > 0)
+                shapes.append(shp)
+                offs.append(off)
+                numel = 1
+                for d in shp:
+                    numel *= d
+                off += (numel + 3) // 4 * 4  # 16-byte aligned slices of one flat buffer
+            lay = self._glay = (shapes, np.asarray(offs, dtype=np.uint64), off)
+        return lay
+
+    def backward(self, dy: torch.Tensor, token: int, needs: List[bool]):
+        """dL/dy -> list of per-tensor gradients (views into ONE flat fp32 buffer, in key order; None where
+        `needs` is False) plus the flat buffer itself (what a data-parallel all-reduce operates on)."""
+        import numpy as np
+        if token != getattr(self, "_train_token", None):
+            raise RuntimeError("RRDBNet backward: the saved activations of this forward were overwritten by a later "
+                               "training forward of the same module (one forward/backward pair at a time)")
+        if dy.dtype != torch.float32 or dy.device != self.device:
+            raise RuntimeError("RRDBNet backward expects an fp32 gradient on the module's device")
+        dy = dy.contiguous()
+        shapes, offs, total = self._grad_layout()
+        flat = torch.empty(total, dtype=torch.float32, device=self.device)
+        ptrs = offs * np.uint64(4) + np.uint64(flat.data_ptr())
+        if not all(needs):
+            ptrs = np.where(np.asarray(needs, dtype=bool), ptrs, np.uint64(0))
+        ptrs = np.ascontiguousarray(ptrs)
+        ws, aligned = self._train_ws
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.esrp_rrdbnet_backward(self.handle, dy.data_ptr(),
+                                                      ptrs.ctypes.data_as(C.POINTER(C.c_void_p)), len(shapes), aligned,
+                                                      torch.cuda.current_stream(self.device).cuda_stream),
+                       "esrp_rrdbnet_backward")
+        self._train_token += 1  # consumed
+        grads = []
+        for shp, off, need in zip(shapes, offs.tolist(), needs):
+            if not need:
+                grads.append(None)
+                continue
+            numel = 1
+            for d in shp:
+                numel *= d
+            grads.append(flat[off:off + numel].view(shp))
+        return grads, flat
+
+    def train_launches(self):
+        return (self.lib.esrp_rrdbnet_train_num_launches(self.handle, 0),
+                self.lib.esrp_rrdbnet_train_num_launches(self.handle, 1))

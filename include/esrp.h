@@ -62,7 +62,7 @@ extern "C" {
  * Training extensions (the autograd backward of the same lines, SRRaGAN_model.py:140,167):
  *   mask_out : bit (mask_out_c0 + ch) of pixel's mask word row <- (acc + bias > 0), the LeakyReLU
  *              derivative selector saved by the forward pass (1 bit per activation);
- *   r2_pre   : r2 is added BEFORE the pre_* stores (v += r2) and s2 becomes a plain final scale;
+ *   r2_pre   : r2 (if any) is added BEFORE the pre_* stores (v += r2) and s2 becomes a plain final scale;
  *   pre_bf16 / pre_f32 : copies of v taken before mask_in / noise / s2 (the gradient of a tensor
  *              that is both an operand of a later launch and the input of an activation);
  *   mask_in  : v *= bit ? 1 : 0.2  (LeakyReLU backward) — applied after the pre_* stores.
@@ -263,6 +263,22 @@ int32_t esrp_rrdbnet_num_launches(const esrp_rrdbnet_t* h);
 int esrp_rrdbnet_forward(esrp_rrdbnet_t* h, const float* x, float* y, int32_t n, int32_t hgt, int32_t w,
                          void* workspace, int64_t workspace_bytes, int32_t training, uint64_t seed,
                          void* stream);
+
+/* ---- training (the autograd graph of architecture.py:76-78 as driven by SRRaGAN_model.py:120,140) ----
+ * esrp_rrdbnet_train_forward computes the same y as esrp_rrdbnet_forward and keeps, in `workspace`, what the
+ * backward needs (per dense block: its bf16 input, x1..x4, one LeakyReLU sign bit per activation; the
+ * upsampled / HR activations of the tail); the GaussianNoise draws are regenerated from (seed, block index).
+ * esrp_rrdbnet_backward must follow on the SAME workspace: dy is NCHW fp32 [n,out_nc,upscale*h,upscale*w];
+ * grads is a HOST array of esrp_rrdbnet_num_tensors() DEVICE pointers (fp32, the shapes of the state_dict
+ * tensors, ordered like esrp_rrdbnet_tensor_key), each OVERWRITTEN with dL/dtensor (NULL entries are skipped).
+ * The gradient w.r.t. x is not produced: the LR input never requires one (SRRaGAN_model.py:103-111). */
+int64_t esrp_rrdbnet_train_workspace_bytes(const esrp_rrdbnet_t* h, int32_t n, int32_t hgt, int32_t w);
+int esrp_rrdbnet_train_forward(esrp_rrdbnet_t* h, const float* x, float* y, int32_t n, int32_t hgt, int32_t w,
+                               void* workspace, int64_t workspace_bytes, int32_t noise, uint64_t seed, void* stream);
+int esrp_rrdbnet_backward(esrp_rrdbnet_t* h, const float* dy, float* const* grads, int32_t count, void* workspace,
+                          void* stream);
+/* Kernel launches of the planned training forward (which = 0) / backward (which = 1). */
+int32_t esrp_rrdbnet_train_num_launches(const esrp_rrdbnet_t* h, int32_t which);
 
 #ifdef __cplusplus
 }
