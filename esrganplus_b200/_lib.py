@@ -123,6 +123,14 @@ SYMBOLS = {
                                      C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "esrp_linear_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int32, C.c_void_p]),
+    "esrp_bn_bwd_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "esrp_bn_bwd_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "esrp_s2d_pad_bwd_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                             C.c_void_p]),
+    "esrp_linear_bwd_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "esrp_pack_dgrad_weights": (C.c_int, [C.POINTER(DgradGroup), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_int32, C.c_void_p, C.c_void_p]),
     "esrp_conv3x3_wgrad": (C.c_int, [C.POINTER(WgradUnit), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

@@ -28,14 +28,25 @@ class _GeneratorFn(torch.autograd.Function):
     def backward(ctx, dy):
         needs = list(ctx.needs_input_grad[5:])
         grads, flat = ctx.eng.backward(dy, ctx.token, needs)
-        group = getattr(ctx.module, "_dp_group", False)
-        if group is not False:
-            import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized():
-                pg = None if group is True else group
-                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=pg)
-                flat.mul_(1.0 / dist.get_world_size(pg))
+        allreduce_flat(ctx.module, flat)
         return (None, None, None, None, None) + tuple(grads)
+
+
+def allreduce_flat(module, flat: torch.Tensor) -> None:
+    """The one exchange step of data-parallel training: average the flat gradient buffer over the ranks of the
+    module's process group (NCCL over NVLink on the GPU box; gloo in the CPU tests).  No-op unless the module was
+    marked by `data_parallel` and torch.distributed is initialised."""
+    group = getattr(module, "_dp_group", False)
+    if group is False:
+        return
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    pg = None if group is True else group
+    ws = dist.get_world_size(pg)
+    if ws > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=pg)
+        flat.mul_(1.0 / ws)
 
 
 def generator_apply(module, x: torch.Tensor, params: Dict[str, torch.Tensor]) -> torch.Tensor:

@@ -248,6 +248,22 @@ __global__ void wgrad_scatter_kernel(const esrp_scatter_entry_t* __restrict__ ta
       continue;
     }
     const int total = s.ncols * s.nci * 9;
+    if (s.kind == 2) {
+      // 4x4 / stride-2 conv evaluated as a 3x3 conv over the space-to-depth tensor (esrp_s2d_pad_nhwc_bf16):
+      // unit channel ci0 + i = (a*2+b) * w_i + ci, tap (A+1, B+1) -> dW4[co][ci][2A+a][2B+b]; taps with A or B < 0 are zero
+      const int ab = s.ci0 / s.w_i, cib = s.ci0 - ab * s.w_i;
+      const int a = ab >> 1, b = ab & 1;
+      for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int tap = i % 9;
+        const int ci = (i / 9) % s.nci;
+        const int c = i / (9 * s.nci);
+        const int A = tap / 3 - 1, B = tap % 3 - 1;
+        if (A < 0 || B < 0) continue;
+        const float v = s.acc[(static_cast<size_t>(tap) * 64 + s.col0 + c) * 32 + ci];
+        dst[s.dst_off + (static_cast<size_t>(s.co0 + c) * s.w_i + cib + ci) * 16 + (2 * A + a) * 4 + (2 * B + b)] = s.scale * v;
+      }
+      continue;
+    }
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
       const int tap = i % 9;
       const int ci = (i / 9) % s.nci;

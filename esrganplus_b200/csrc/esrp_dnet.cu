@@ -158,3 +158,199 @@ int esrp_linear_f32(const float* x, const float* w, const float* bias, float* y,
 }
 
 }  // extern "C"
+
+// =================================================================================================
+// Backward pieces of Discriminator_VGG_128 (autograd of architecture.py:87-129 as driven by
+// SRRaGAN_model.py:140,167): BatchNorm2d(train) + LeakyReLU backward as a reduction pass and an apply
+// pass, the inverse of the space-to-depth rearrangement, and the two Linear layers.
+// =================================================================================================
+namespace esrp {
+
+// coef layout: [7][c] fp32 = mean, rstd, scale (gamma*rstd), shift, g_rs (gamma*rstd), a (sum dzb / N), b (sum dzb*xhat / N)
+__device__ __forceinline__ float bn_dzb(float z, float d, float scale, float shift) {
+  const float zb = fmaf(z, scale, shift);
+  return zb > 0.f ? d : 0.2f * d;
+}
+
+// sums[ch] += sum dzb, sums[c+ch] += sum dzb * xhat over the valid [h, w] region.
+// dout: bf16 NHWC [n,h,w,c] (dout_nchw == NULL) or fp32 NCHW-flat [n, c*h*w].
+__global__ void bn_bwd_reduce_kernel(const float* __restrict__ z, const __nv_bfloat16* __restrict__ dout,
+                                     const float* __restrict__ dout_nchw, int n, int h, int w, int hp, int wp, int c,
+                                     const float* __restrict__ coef, double* __restrict__ sums) {
+  const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int lane_px = threadIdx.x >> 5;
+  const long long npx = static_cast<long long>(n) * h * w;
+  double s1 = 0.0, s2 = 0.0;
+  if (ch < c) {
+    const float mean = coef[ch], rstd = coef[c + ch], scale = coef[2 * c + ch], shift = coef[3 * c + ch];
+    for (long long pi = static_cast<long long>(blockIdx.y) * 8 + lane_px; pi < npx; pi += static_cast<long long>(gridDim.y) * 8) {
+      const int xw = static_cast<int>(pi % w);
+      const long long t = pi / w;
+      const int yh = static_cast<int>(t % h);
+      const int img = static_cast<int>(t / h);
+      const float zv = z[((static_cast<size_t>(img) * hp + yh) * wp + xw) * c + ch];
+      const float d = dout_nchw ? dout_nchw[((static_cast<size_t>(img) * c + ch) * h + yh) * w + xw]
+                                : __bfloat162float(dout[static_cast<size_t>(pi) * c + ch]);
+      const float dzb = bn_dzb(zv, d, scale, shift);
+      s1 += dzb;
+      s2 += static_cast<double>(dzb) * ((zv - mean) * rstd);
+    }
+  }
+  __shared__ double sh[2][8][32];
+  sh[0][lane_px][threadIdx.x & 31] = s1;
+  sh[1][lane_px][threadIdx.x & 31] = s2;
+  __syncthreads();
+  if (lane_px == 0 && ch < c) {
+    for (int i = 1; i < 8; ++i) { s1 += sh[0][i][threadIdx.x & 31]; s2 += sh[1][i][threadIdx.x & 31]; }
+    atomicAdd(&sums[ch], s1);
+    atomicAdd(&sums[c + ch], s2);
+  }
+}
+
+// dz[n,hp,wp,c] (bf16, the conv's output grid; zero outside the valid region) = g_rs * (dzb - a - xhat * b)
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ z, const __nv_bfloat16* __restrict__ dout,
+                                    const float* __restrict__ dout_nchw, int n, int h, int w, int hp, int wp, int c,
+                                    const float* __restrict__ coef, __nv_bfloat16* __restrict__ dz) {
+  const size_t total = static_cast<size_t>(n) * hp * wp * c;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % c);
+    size_t t = i / c;
+    const int xw = static_cast<int>(t % wp); t /= wp;
+    const int yh = static_cast<int>(t % hp);
+    const int img = static_cast<int>(t / hp);
+    float v = 0.f;
+    if (yh < h && xw < w) {
+      const float zv = z[i];
+      const float d = dout_nchw ? dout_nchw[((static_cast<size_t>(img) * c + ch) * h + yh) * w + xw]
+                                : __bfloat162float(dout[((static_cast<size_t>(img) * h + yh) * w + xw) * c + ch]);
+      const float dzb = bn_dzb(zv, d, coef[2 * c + ch], coef[3 * c + ch]);
+      const float xhat = (zv - coef[ch]) * coef[c + ch];
+      v = coef[4 * c + ch] * (dzb - coef[5 * c + ch] - xhat * coef[6 * c + ch]);
+    }
+    dz[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// Inverse of s2d_pad_kernel: din[n, y, x, ch] = ds[n, (y+1)>>1, (x+1)>>1, (((y+1)&1)*2 + ((x+1)&1))*c + ch],
+// optionally times the LeakyReLU derivative selected by the sign of `ref` (the bf16 activation that was fed forward).
+__global__ void s2d_pad_bwd_kernel(const uint4* __restrict__ ds, uint4* __restrict__ din, const uint4* __restrict__ ref,
+                                   int n, int h, int w, int cv) {
+  const int ho = h / 2 + 1, wo = w / 2 + 1;
+  const size_t total = static_cast<size_t>(n) * h * w * cv;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % cv);
+    size_t t = i / cv;
+    const int x = static_cast<int>(t % w); t /= w;
+    const int y = static_cast<int>(t % h);
+    const int img = static_cast<int>(t / h);
+    const int Y = (y + 1) >> 1, a = (y + 1) & 1, X = (x + 1) >> 1, b = (x + 1) & 1;
+    uint4 q = __ldg(ds + ((static_cast<size_t>(img) * ho + Y) * wo + X) * 4 * cv + (a * 2 + b) * cv + v);
+    if (ref) {
+      const uint4 r = __ldg(ref + i);
+      uint32_t qs[4] = {q.x, q.y, q.z, q.w};
+      const uint32_t rs[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float lo = __uint_as_float(qs[j] << 16), hi = __uint_as_float(qs[j] & 0xFFFF0000u);
+        const float rlo = __uint_as_float(rs[j] << 16), rhi = __uint_as_float(rs[j] & 0xFFFF0000u);
+        if (!(rlo > 0.f)) lo *= 0.2f;
+        if (!(rhi > 0.f)) hi *= 0.2f;
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+        qs[j] = *reinterpret_cast<const uint32_t*>(&h2);
+      }
+      q = make_uint4(qs[0], qs[1], qs[2], qs[3]);
+    }
+    din[i] = q;
+  }
+}
+
+// Linear backward.  dym = dy * lrelu'(yout) when yout != NULL (yout = the layer's activated output).
+// mode 0: dx[b,k] = sum_o dym[b,o] w[o,k];  mode 1: dw[o,k] = sum_b dym[b,o] x[b,k];  mode 2: db[o] = sum_b dym[b,o]
+__global__ void linear_bwd_kernel(int mode, const float* __restrict__ dy, const float* __restrict__ yout,
+                                  const float* __restrict__ x, const float* __restrict__ wgt, float* __restrict__ out,
+                                  int b, int k, int o) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  auto dym = [&](int bi, int oi) {
+    const float d = dy[static_cast<size_t>(bi) * o + oi];
+    return (yout && !(yout[static_cast<size_t>(bi) * o + oi] > 0.f)) ? 0.2f * d : d;
+  };
+  if (mode == 0) {
+    if (idx >= static_cast<size_t>(b) * k) return;
+    const int bi = static_cast<int>(idx / k), ki = static_cast<int>(idx % k);
+    float acc = 0.f;
+    for (int oi = 0; oi < o; ++oi) acc = fmaf(dym(bi, oi), wgt[static_cast<size_t>(oi) * k + ki], acc);
+    out[idx] = acc;
+  } else if (mode == 1) {
+    if (idx >= static_cast<size_t>(o) * k) return;
+    const int oi = static_cast<int>(idx / k), ki = static_cast<int>(idx % k);
+    float acc = 0.f;
+    for (int bi = 0; bi < b; ++bi) acc = fmaf(dym(bi, oi), x[static_cast<size_t>(bi) * k + ki], acc);
+    out[idx] = acc;
+  } else {
+    if (idx >= static_cast<size_t>(o)) return;
+    float acc = 0.f;
+    for (int bi = 0; bi < b; ++bi) acc += dym(bi, static_cast<int>(idx));
+    out[idx] = acc;
+  }
+}
+
+}  // namespace esrp
+
+extern "C" {
+
+int esrp_bn_bwd_reduce(const float* z, const void* dout_bf16, const float* dout_nchw_f32, int32_t n, int32_t h, int32_t w,
+                       int32_t hp, int32_t wp, int32_t c, const float* coef7c, double* sums2c, void* stream) {
+  if (!z || (!dout_bf16 && !dout_nchw_f32) || !coef7c || !sums2c || h > hp || w > wp) return esrp::set_error("bn_bwd_reduce: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ESRP_CUDA_OK(cudaMemsetAsync(sums2c, 0, sizeof(double) * 2 * c, s));
+  const long long npx = static_cast<long long>(n) * h * w;
+  int slabs = static_cast<int>((npx + 8 * 64 - 1) / (8 * 64));
+  if (slabs > 296) slabs = 296;
+  if (slabs < 1) slabs = 1;
+  dim3 grid((c + 31) / 32, slabs);
+  esrp::bn_bwd_reduce_kernel<<<grid, 256, 0, s>>>(z, static_cast<const __nv_bfloat16*>(dout_bf16), dout_nchw_f32, n, h, w, hp,
+                                                  wp, c, coef7c, sums2c);
+  ESRP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int esrp_bn_bwd_apply(const float* z, const void* dout_bf16, const float* dout_nchw_f32, int32_t n, int32_t h, int32_t w,
+                      int32_t hp, int32_t wp, int32_t c, const float* coef7c, void* dz_bf16, void* stream) {
+  if (!z || (!dout_bf16 && !dout_nchw_f32) || !coef7c || !dz_bf16 || h > hp || w > wp) return esrp::set_error("bn_bwd_apply: bad arguments");
+  const size_t total = static_cast<size_t>(n) * hp * wp * c;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  esrp::bn_bwd_apply_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      z, static_cast<const __nv_bfloat16*>(dout_bf16), dout_nchw_f32, n, h, w, hp, wp, c, coef7c,
+      static_cast<__nv_bfloat16*>(dz_bf16));
+  ESRP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int esrp_s2d_pad_bwd_nhwc_bf16(const void* ds, void* din, const void* lrelu_ref, int32_t n, int32_t h, int32_t w, int32_t c,
+                               void* stream) {
+  if (!ds || !din || (c % 8) || (h % 2) || (w % 2)) return esrp::set_error("s2d_pad_bwd: c %% 8, h %% 2, w %% 2 must be 0");
+  const int cv = c / 8;
+  const size_t total = static_cast<size_t>(n) * h * w * cv;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  esrp::s2d_pad_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(ds), static_cast<uint4*>(din), static_cast<const uint4*>(lrelu_ref), n, h, w, cv);
+  ESRP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int esrp_linear_bwd_f32(const float* dy, const float* yout_act, const float* x, const float* w, float* dx, float* dw, float* db,
+                        int32_t b, int32_t k, int32_t o, void* stream) {
+  if (!dy || !x || !w) return esrp::set_error("linear_bwd: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dx) esrp::linear_bwd_kernel<<<(static_cast<size_t>(b) * k + 255) / 256, 256, 0, s>>>(0, dy, yout_act, x, w, dx, b, k, o);
+  if (dw) esrp::linear_bwd_kernel<<<(static_cast<size_t>(o) * k + 255) / 256, 256, 0, s>>>(1, dy, yout_act, x, w, dw, b, k, o);
+  if (db) esrp::linear_bwd_kernel<<<(o + 255) / 256, 256, 0, s>>>(2, dy, yout_act, x, w, db, b, k, o);
+  ESRP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -11,18 +11,31 @@ does the O(C) BatchNorm bookkeeping on [C]-sized vectors (mean/var -> scale/shif
 * Output channels are cut in slices of 32 and K in groups of chunks whose weights fit in shared memory;
   later K groups accumulate onto the fp32 result of the earlier ones through the residual input.
 
-Forward only (inference and the no-grad D passes); the backward pass is not built yet.
+Backward (SRRaGAN_model.py:140 G phase: data gradient only, D frozen; :167 D phase: everything): per layer,
+BatchNorm(train)+LeakyReLU backward as a reduction + an apply pass that writes dz (bf16) on the conv's output
+grid, the weight gradient as conv3x3_wgrad units (32 input channels x 64 output channels x 9 taps; a 4x4 conv's
+units are scattered through the space-to-depth index map), the data gradient as esrp_conv3x3_nhwc over
+esrp_pack_dgrad_weights, and for the stride-2 layers the inverse space-to-depth rearrangement.  Parameter
+gradients are views of ONE flat fp32 buffer (what the data-parallel all-reduce operates on).
 """
 from __future__ import annotations
 
 import ctypes as C
 from typing import Dict, List, Optional, Tuple
 
+import numpy as np
 import torch
 import torch.nn as nn
 
 from . import _lib
 from . import conv as K
+
+_UNIT_DT = np.dtype([("x", "u8"), ("x_ctotal", "i4"), ("x_c0", "i4"), ("dy", "u8"), ("dy_ctotal", "i4"), ("dy_c0", "i4"),
+                     ("acc", "u8"), ("bias_acc", "u8")], align=True)
+_SCAT_DT = np.dtype([("acc", "u8"), ("dst", "u8"), ("dst_off", "i8"), ("dst_index", "i4"), ("kind", "i4"), ("col0", "i4"),
+                     ("ncols", "i4"), ("nci", "i4"), ("co0", "i4"), ("ci0", "i4"), ("w_i", "i4"), ("scale", "f4")], align=True)
+assert _UNIT_DT.itemsize == C.sizeof(_lib.WgradUnit) and _SCAT_DT.itemsize == C.sizeof(_lib.ScatterEntry)
+ACC_BLOCK = 9 * 64 * 32
 
 SLICE = 32            # output channels per launch
 MAX_CHUNKS = {_lib.LAYOUT_ROW: 3, _lib.LAYOUT_TILE: 8}   # K chunks per launch (weights must fit in smem)
@@ -53,6 +66,8 @@ class _Layer:
         if (self.k, self.stride) not in ((3, 1), (4, 2)) or self.cout % SLICE:
             raise NotImplementedError("Discriminator_VGG_128: only k3s1 / k4s2 convs with Cout % 32 == 0")
         self.packed: Dict[Tuple[int, int, int], torch.Tensor] = {}   # (layout, slice, kgroup) -> packed weights
+        self.packed_t: Dict[Tuple[int, int], torch.Tensor] = {}      # (layout, input-channel slice) -> dgrad weights
+        self.wg_tab = None                                           # cached wgrad unit / scatter tables
         self.bias_pad: Optional[torch.Tensor] = None
         self.w3: Optional[torch.Tensor] = None
         self.sig = None
@@ -92,6 +107,7 @@ class DiscriminatorEngine:
             L.cin_eff = L.w3.shape[1]
             L.bias_pad = torch.zeros(L.cout, device=self.device) if b is None else b.detach().clone()
         L.packed.clear()
+        L.packed_t.clear()
         L.sig = sig
 
     def _packed(self, L: _Layer, layout: int, s: int, g: int, chunks: List[int]) -> torch.Tensor:
@@ -103,7 +119,7 @@ class DiscriminatorEngine:
         return t
 
     # -- one conv layer: NHWC bf16 [n,h,w,cin_pad] -> fp32 NHWC on the conv grid (or bf16 when fused) ------
-    def _conv(self, L: _Layer, act: torch.Tensor, fuse_act_bf16: bool):
+    def _conv(self, L: _Layer, act: torch.Tensor, fuse_act_bf16: bool, keep: Optional[list] = None):
         n, h, w, c = act.shape
         if L.k == 4:
             src = torch.empty((n, h // 2 + 1, w // 2 + 1, 4 * c), dtype=torch.bfloat16, device=self.device)
@@ -113,6 +129,8 @@ class DiscriminatorEngine:
             src, hv, wv = act, h, w
         gh, gw = src.shape[1], src.shape[2]
         assert src.shape[3] == L.cin_eff, (src.shape, L.cin_eff)
+        if keep is not None:
+            keep.append(src)   # the conv's operand: what the weight gradient contracts against
         layout = _lib.LAYOUT_ROW if gw > 64 else _lib.LAYOUT_TILE
         nchunks = L.cin_eff // L.kc
         per = MAX_CHUNKS[layout]
@@ -138,7 +156,7 @@ class DiscriminatorEngine:
         return (out_b if fused else out_f), hv, wv
 
     # -- forward ---------------------------------------------------------------------------------
-    def forward(self, module: nn.Module, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, module: nn.Module, x: torch.Tensor, saved: Optional[list] = None) -> torch.Tensor:
         if x.dim() != 4 or x.dtype != torch.float32 or x.device != self.device:
             raise RuntimeError("Discriminator_VGG_128 forward expects an fp32 NCHW CUDA tensor")
         n = x.shape[0]
@@ -149,10 +167,16 @@ class DiscriminatorEngine:
         for li, L in enumerate(self.layers):
             self._sync(L)
             is_last = li == len(self.layers) - 1
-            y, hv, wv = self._conv(L, act, fuse_act_bf16=L.bn is None)
+            y, hv, wv = self._conv(L, act, fuse_act_bf16=L.bn is None, keep=saved)
+            rec = None
+            if saved is not None:
+                rec = dict(src=saved.pop(), in_shape=tuple(act.shape), y=None, hv=hv, wv=wv)
+                saved.append(rec)
             if L.bn is None:
                 act = y[:, :hv, :wv, :] if (y.shape[1] != hv or y.shape[2] != wv) else y
                 act = act.contiguous()
+                if rec is not None:
+                    rec["out_act"] = act
                 continue
             gh, gw, c = y.shape[1], y.shape[2], L.cout
             bn = L.bn
@@ -175,6 +199,9 @@ class DiscriminatorEngine:
                 rstd = torch.rsqrt(var + bn.eps)
                 scale = (bn.weight.detach().double() * rstd).float().contiguous()
                 shift = (bn.bias.detach().double() - mean * bn.weight.detach().double() * rstd).float().contiguous()
+                if rec is not None:
+                    rec.update(y=y, mean=mean.float(), rstd=rstd.float(), scale=scale, shift=shift, count=count,
+                               batch_stats=bool(bn.training))
             nxt = torch.empty((n, hv, wv, c), dtype=torch.bfloat16, device=self.device)
             if is_last:
                 flat = torch.empty((n, c * hv * wv), dtype=torch.float32, device=self.device)
@@ -188,18 +215,209 @@ class DiscriminatorEngine:
             wt = fc.weight.detach().contiguous()
             _lib.check(self.lib.esrp_linear_f32(src.data_ptr(), wt.data_ptr(), fc.bias.data_ptr() if fc.bias is not None else None,
                                                 dst.data_ptr(), n, fc.in_features, fc.out_features, a, _stream()), "linear")
+        if saved is not None:
+            saved.append(dict(flat=flat, h0=h0, n=n))
         return out
+
+    # -- backward --------------------------------------------------------------------------------
+    def _dgrad_packed(self, L: _Layer, layout: int, s: int, kc: int) -> torch.Tensor:
+        key = (layout, s)
+        t = L.packed_t.get(key)
+        if t is None:
+            groups = [(L.w3, 32 * g, 1.0) for g in range(L.cout // 32)]
+            t = K.pack_dgrad_weights(groups, s * SLICE, min(SLICE, L.cin_eff - s * SLICE), kc, SLICE, layout=layout)
+            L.packed_t[key] = t
+        return t
+
+    def _wgrad_tables(self, L: _Layer):
+        """Static part of the layer's wgrad unit table and scatter table (pointers are patched per call)."""
+        if L.wg_tab is None:
+            ng, nblk = L.cin_eff // 32, L.cout // 64
+            units = np.zeros(ng * nblk, dtype=_UNIT_DT)
+            scat = np.zeros(ng * nblk + nblk, dtype=_SCAT_DT)
+            real_cin = L.cin
+            i = 0
+            for g in range(ng):
+                for b in range(nblk):
+                    units[i]["x_ctotal"], units[i]["x_c0"] = L.cin_eff, 32 * g
+                    units[i]["dy_ctotal"], units[i]["dy_c0"] = L.cout, 64 * b
+                    e = scat[i]
+                    e["dst_index"], e["col0"], e["ncols"], e["co0"], e["ci0"], e["w_i"], e["scale"] = -1, 0, 64, 64 * b, 32 * g, real_cin, 1.0
+                    if L.k == 3:
+                        e["kind"] = 0
+                        e["nci"] = max(0, min(32, real_cin - 32 * g))
+                    else:
+                        e["kind"], e["nci"] = 2, 32
+                    i += 1
+            for b in range(nblk):
+                e = scat[ng * nblk + b]
+                e["dst_index"], e["kind"], e["ncols"], e["scale"], e["dst_off"] = -1, 1, 64, 1.0, 64 * b
+            L.wg_tab = (units, scat, ng, nblk)
+        return L.wg_tab
+
+    def _wgrad(self, L: _Layer, src: torch.Tensor, dz: torch.Tensor, dw: torch.Tensor, db: torch.Tensor) -> None:
+        units0, scat0, ng, nblk = self._wgrad_tables(L)
+        n, gh, gw, _ = dz.shape
+        nu = ng * nblk
+        acc = torch.zeros(nu * ACC_BLOCK + nblk * 64, dtype=torch.float32, device=self.device)
+        units, scat = units0.copy(), scat0.copy()
+        accp = acc.data_ptr()
+        bias_base = accp + 4 * nu * ACC_BLOCK
+        idx = np.arange(nu, dtype=np.uint64)
+        units["x"], units["dy"] = src.data_ptr(), dz.data_ptr()
+        units["acc"] = np.uint64(accp) + idx * np.uint64(4 * ACC_BLOCK)
+        blk = (idx % np.uint64(nblk))
+        units["bias_acc"] = np.where(idx < np.uint64(nblk), np.uint64(bias_base) + blk * np.uint64(256), np.uint64(0))
+        scat["acc"][:nu] = units["acc"]
+        scat["dst"][:nu] = dw.data_ptr()
+        scat["acc"][nu:] = np.uint64(bias_base) + np.arange(nblk, dtype=np.uint64) * np.uint64(256)
+        scat["dst"][nu:] = db.data_ptr()
+        st = _stream()
+        for u0 in range(0, nu, _lib.WGRAD_MAX_UNITS):
+            cnt = min(_lib.WGRAD_MAX_UNITS, nu - u0)
+            part = np.ascontiguousarray(units[u0:u0 + cnt])
+            _lib.check(self.lib.esrp_conv3x3_wgrad(part.ctypes.data_as(C.POINTER(_lib.WgradUnit)), cnt, n, gh, gw, 0, st),
+                       "esrp_conv3x3_wgrad")
+        if L.k == 3 and L.cin % 32:
+            dw.zero_()  # (never the case for D_VGG_128 beyond layer 0, whose 3 real channels are all written)
+        _lib.check(self.lib.esrp_wgrad_scatter(scat.ctypes.data_as(C.POINTER(_lib.ScatterEntry)), len(scat), st),
+                   "esrp_wgrad_scatter")
+
+    def _dgrad(self, L: _Layer, dz: torch.Tensor, out_nchw: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        """dz [n,gh,gw,cout] bf16 -> gradient of the conv's (space-to-depth) input [n,gh,gw,cin_eff] bf16, or for the
+        first layer straight into the NCHW fp32 gradient of the image."""
+        n, gh, gw, _ = dz.shape
+        layout = _lib.LAYOUT_ROW if gw > 64 else _lib.LAYOUT_TILE
+        kc = 64 if L.cout % 64 == 0 else 32
+        nchunks = L.cout // kc
+        if nchunks > MAX_CHUNKS[layout]:
+            raise NotImplementedError("Discriminator_VGG_128 backward: K does not fit one launch for this layer width")
+        chunks = [(0, c * kc) for c in range(nchunks)]
+        if out_nchw is not None:
+            wp = L.packed_t.get((layout, -1))
+            if wp is None:
+                groups = [(L.w3, 32 * g, 1.0) for g in range(L.cout // 32)]
+                wp = K.pack_dgrad_weights(groups, 0, L.cin, kc, 16, layout=layout)
+                L.packed_t[(layout, -1)] = wp
+            K.ConvCall(n=n, h=gh, w=gw, srcs=[dz], kc=kc, chunks=chunks, bn=16, cout=L.cin, w_packed=wp, w_layout=layout,
+                       out_nchw=out_nchw).launch()
+            return None
+        out = torch.empty((n, gh, gw, L.cin_eff), dtype=torch.bfloat16, device=self.device)
+        for s in range(L.cin_eff // SLICE):
+            K.ConvCall(n=n, h=gh, w=gw, srcs=[dz], kc=kc, chunks=chunks, bn=SLICE, cout=SLICE,
+                       w_packed=self._dgrad_packed(L, layout, s, kc), w_layout=layout, out_bf16=out, ob_c0=s * SLICE).launch()
+        return out
+
+    def backward(self, module: nn.Module, saved: list, dout: torch.Tensor, need_dx: bool, need_params: bool):
+        """Returns (dx NCHW fp32 or None, {parameter name: gradient view} or {}, flat gradient buffer or None)."""
+        st = _stream()
+        head = saved[-1]
+        n, flat, h0 = head["n"], head["flat"], head["h0"]
+        names = [k for k, _ in module.named_parameters()]
+        params = dict(module.named_parameters())
+        grads: Dict[str, torch.Tensor] = {}
+        flatg = None
+        if need_params:
+            offs, off = {}, 0
+            for k in names:
+                offs[k] = off
+                off += (params[k].numel() + 3) // 4 * 4
+            flatg = torch.empty(off, dtype=torch.float32, device=self.device)
+            grads = {k: flatg[offs[k]:offs[k] + params[k].numel()].view(params[k].shape) for k in names}
+        gp = lambda k: grads[k].data_ptr() if need_params else None
+        dout = dout.contiguous().float()
+        # classifier (architecture.py:122-123)
+        dh0 = torch.empty_like(h0)
+        _lib.check(self.lib.esrp_linear_bwd_f32(dout.data_ptr(), None, h0.data_ptr(), self.fc1.weight.data_ptr(), dh0.data_ptr(),
+                                                gp("classifier.2.weight"), gp("classifier.2.bias"), n, self.fc1.in_features,
+                                                self.fc1.out_features, st), "linear_bwd")
+        dflat = torch.empty_like(flat)
+        _lib.check(self.lib.esrp_linear_bwd_f32(dh0.data_ptr(), h0.data_ptr(), flat.data_ptr(), self.fc0.weight.data_ptr(),
+                                                dflat.data_ptr(), gp("classifier.0.weight"), gp("classifier.0.bias"), n,
+                                                self.fc0.in_features, self.fc0.out_features, st), "linear_bwd")
+        feats = list(module.features)
+        idx_of = {id(m): i for i, m in enumerate(feats)}
+        dout_b, dout_nchw = None, dflat
+        dx = None
+        for li in range(len(self.layers) - 1, -1, -1):
+            L, rec = self.layers[li], saved[li]
+            ci = idx_of[id(L.conv)]
+            hv, wv, c = rec["hv"], rec["wv"], L.cout
+            if L.bn is not None:
+                y = rec["y"]
+                gh, gw = y.shape[1], y.shape[2]
+                bi = idx_of[id(L.bn)]
+                gamma = L.bn.weight.detach()
+                coef = torch.zeros((7, c), dtype=torch.float32, device=self.device)
+                coef[0], coef[1], coef[2], coef[3] = rec["mean"], rec["rstd"], rec["scale"], rec["shift"]
+                coef[4] = gamma * rec["rstd"]
+                sums = torch.empty(2 * c, dtype=torch.float64, device=self.device)
+                db_, dn_ = (dout_b.data_ptr() if dout_b is not None else None), (dout_nchw.data_ptr() if dout_nchw is not None else None)
+                _lib.check(self.lib.esrp_bn_bwd_reduce(y.data_ptr(), db_, dn_, n, hv, wv, gh, gw, c, coef.data_ptr(),
+                                                       sums.data_ptr(), st), "bn_bwd_reduce")
+                if rec["batch_stats"]:
+                    coef[5] = (sums[:c] / rec["count"]).float()
+                    coef[6] = (sums[c:] / rec["count"]).float()
+                if need_params:
+                    grads[f"features.{bi}.weight"].copy_(sums[c:])
+                    grads[f"features.{bi}.bias"].copy_(sums[:c])
+                dz = torch.empty((n, gh, gw, c), dtype=torch.bfloat16, device=self.device)
+                _lib.check(self.lib.esrp_bn_bwd_apply(y.data_ptr(), db_, dn_, n, hv, wv, gh, gw, c, coef.data_ptr(),
+                                                      dz.data_ptr(), st), "bn_bwd_apply")
+            else:
+                dz = dout_b  # already times lrelu' (s2d_pad_bwd with the forward activation as sign reference)
+            if need_params:
+                self._wgrad(L, rec["src"], dz, grads[f"features.{ci}.weight"], grads[f"features.{ci}.bias"])
+            if li == 0:
+                if need_dx:
+                    dx = torch.empty((n, L.cin, dz.shape[1], dz.shape[2]), dtype=torch.float32, device=self.device)
+                    self._dgrad(L, dz, dx)
+                break
+            dsrc = self._dgrad(L, dz, None)
+            if L.k == 4:
+                _, ih, iw, ic = rec["in_shape"]
+                din = torch.empty((n, ih, iw, ic), dtype=torch.bfloat16, device=self.device)
+                prev = self.layers[li - 1]
+                ref = saved[li - 1]["out_act"] if prev.bn is None else None
+                _lib.check(self.lib.esrp_s2d_pad_bwd_nhwc_bf16(dsrc.data_ptr(), din.data_ptr(), ref.data_ptr() if ref is not None else None,
+                                                               n, ih, iw, ic, st), "s2d_pad_bwd")
+            else:
+                if self.layers[li - 1].bn is None:
+                    raise NotImplementedError("Discriminator_VGG_128 backward: an un-normalised layer must feed a stride-2 layer")
+                din = dsrc
+            dout_b, dout_nchw = din, None
+        return dx, grads, flatg
+
+
+class _DiscriminatorFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, eng, x, *params):
+        saved: list = []
+        out = eng.forward(module, x, saved)
+        ctx.module, ctx.eng, ctx.saved = module, eng, saved
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        need_dx = ctx.needs_input_grad[2]
+        needs = ctx.needs_input_grad[3:]
+        need_params = any(needs)
+        dx, grads, flat = ctx.eng.backward(ctx.module, ctx.saved, dout, need_dx, need_params)
+        ctx.saved = None
+        if flat is not None:
+            from .autograd import allreduce_flat
+            allreduce_flat(ctx.module, flat)
+        names = [k for k, _ in ctx.module.named_parameters()]
+        return (None, None, dx) + tuple(grads[k] if (need_params and nd) else None for k, nd in zip(names, needs))
 
 
 def discriminator_apply(module: nn.Module, x: torch.Tensor) -> torch.Tensor:
     needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters()))
-    if needs_grad:
-        raise NotImplementedError(
-            "esrganplus_b200: the Discriminator_VGG_128 backward pass is not built yet; call it under "
-            "torch.no_grad() (forward only)")
     engines = module.__dict__.setdefault("_engines", {})
     eng = engines.get(x.device)
     if eng is None:
         eng = DiscriminatorEngine(module, x.device)
         engines[x.device] = eng
+    if needs_grad:
+        return _DiscriminatorFn.apply(module, eng, x.contiguous(), *[p for _, p in module.named_parameters()])
     return eng.forward(module, x.contiguous())

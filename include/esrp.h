@@ -171,6 +171,25 @@ int esrp_bn_stats_nhwc_f32(const float* x, int32_t n, int32_t h, int32_t w, int3
 int esrp_bn_apply_nhwc(const float* x, int32_t n, int32_t h, int32_t w, int32_t hp, int32_t wp, int32_t c,
                        const float* scale, const float* shift, int32_t act, void* out_bf16,
                        float* out_nchw_f32, void* stream);
+/* Backward of BatchNorm2d (batch statistics) + LeakyReLU(0.2) over the valid [h,w] region of the conv output z
+ * [n,hp,wp,c] fp32.  dout is the gradient of the activated output: bf16 NHWC [n,h,w,c], or (when dout_bf16 is
+ * NULL) fp32 in NCHW-flattened order [n, c*h*w] (the classifier's input gradient).  coef7c = fp32 [7][c]:
+ * mean, rstd, scale = gamma*rstd, shift = beta - mean*scale, g_rs = gamma*rstd, a, b.  With dzb = dout * lrelu'(z*scale+shift):
+ *   reduce: sums2c[ch] = sum dzb (= d beta), sums2c[c+ch] = sum dzb * xhat (= d gamma), xhat = (z - mean) * rstd
+ *   apply : dz = g_rs * (dzb - a - xhat * b)  (a = sum dzb / N, b = sum dzb*xhat / N; a = b = 0 for eval-mode BN),
+ *           written as bf16 on the whole [n,hp,wp,c] grid, zero outside the valid region. */
+int esrp_bn_bwd_reduce(const float* z, const void* dout_bf16, const float* dout_nchw_f32, int32_t n, int32_t h, int32_t w,
+                       int32_t hp, int32_t wp, int32_t c, const float* coef7c, double* sums2c, void* stream);
+int esrp_bn_bwd_apply(const float* z, const void* dout_bf16, const float* dout_nchw_f32, int32_t n, int32_t h, int32_t w,
+                      int32_t hp, int32_t wp, int32_t c, const float* coef7c, void* dz_bf16, void* stream);
+/* Inverse of esrp_s2d_pad_nhwc_bf16 (gradient of the rearrangement): ds [n,h/2+1,w/2+1,4c] -> din [n,h,w,c];
+ * lrelu_ref (optional, bf16 [n,h,w,c]): din *= (ref > 0 ? 1 : 0.2), the LeakyReLU derivative of the activation fed forward. */
+int esrp_s2d_pad_bwd_nhwc_bf16(const void* ds, void* din, const void* lrelu_ref, int32_t n, int32_t h, int32_t w, int32_t c,
+                               void* stream);
+/* nn.Linear backward; yout_act (optional) = the layer's LeakyReLU-activated output (dy is masked by its sign).
+ * dx [b,k], dw [o,k], db [o]: each optional. */
+int esrp_linear_bwd_f32(const float* dy, const float* yout_act, const float* x, const float* w, float* dx, float* dw, float* db,
+                        int32_t b, int32_t k, int32_t o, void* stream);
 /* nn.Linear (+ optional LeakyReLU 0.2): y[b,o] = sum_k x[b,k] w[o,k] + bias[o]  (architecture.py:122-123). */
 int esrp_linear_f32(const float* x, const float* w, const float* bias, float* y, int32_t b, int32_t k, int32_t o,
                     int32_t act, void* stream);
@@ -211,7 +230,9 @@ typedef struct esrp_wgrad_unit {
 int esrp_conv3x3_wgrad(const esrp_wgrad_unit_t* units_host, int32_t num_units, int32_t n, int32_t h, int32_t w,
                        int32_t splits, void* stream);
 /* kind 0: dst[dst_off + ((co0 + c) * w_i + ci0 + i) * 9 + tap] = scale * acc[tap][col0 + c][i], c < ncols, i < nci
- * kind 1: dst[dst_off + i] = scale * acc[i], i < ncols.  dst_index is used by the engines only. */
+ * kind 1: dst[dst_off + i] = scale * acc[i], i < ncols.  dst_index is used by the engines only.
+ * kind 2: a 4x4 / stride-2 conv run as a 3x3 conv over the space-to-depth tensor: unit channel ci0 + i =
+ *         (a*2+b) * w_i + ci and tap (A+1, B+1) go to dst[((co0 + c) * w_i + ci) * 16 + (2A+a) * 4 + 2B+b]. */
 typedef struct esrp_scatter_entry {
   const float* acc;
   float* dst;

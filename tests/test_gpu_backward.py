@@ -159,3 +159,43 @@ def test_upsample2x_bwd(cuda_dev):
     assert (of - s).abs().max().item() <= 1e-5
     want = s * torch.where(bits, 1.0, 0.2)
     assert (ob.float() - want).abs().max().item() <= 1e-2 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("cin,cout,hw", [(64, 64, 16), (128, 128, 8)])
+def test_k4s2_layer_gradients_match_conv2d_autograd(cuda_dev, cin, cout, hw):
+    """A 4x4 / stride-2 / pad-1 conv (architecture.py:95-119) runs as a 3x3 conv over the space-to-depth tensor:
+    weight gradient = conv3x3_wgrad units scattered through the (a, b, tap) -> 4x4 index map (scatter kind 2),
+    data gradient = transposed 3x3 conv + inverse space-to-depth; both against torch conv2d(stride=2) autograd on the
+    same bf16 operands."""
+    import torch.nn as nn
+    from esrganplus_b200.discriminator import DiscriminatorEngine, _Layer
+    n = 2
+    g = torch.Generator(device=cuda_dev).manual_seed(cin + hw)
+    conv = nn.Conv2d(cin, cout, 4, 2, 1).to(cuda_dev)
+    eng = DiscriminatorEngine.__new__(DiscriminatorEngine)
+    eng.lib, eng.device = _lib.load(), cuda_dev
+    L = _Layer(conv, None)
+    eng._sync(L)
+    act = torch.randn(n, hw, hw, cin, device=cuda_dev, generator=g).to(torch.bfloat16)
+    src = torch.empty(n, hw // 2 + 1, hw // 2 + 1, 4 * cin, device=cuda_dev, dtype=torch.bfloat16)
+    assert eng.lib.esrp_s2d_pad_nhwc_bf16(act.data_ptr(), src.data_ptr(), n, hw, hw, cin, torch.cuda.current_stream().cuda_stream) == 0
+    dz = torch.zeros(n, hw // 2 + 1, hw // 2 + 1, cout, device=cuda_dev, dtype=torch.bfloat16)
+    dz[:, :hw // 2, :hw // 2] = torch.randn(n, hw // 2, hw // 2, cout, device=cuda_dev, generator=g).to(torch.bfloat16)
+    dw = torch.full_like(conv.weight, float("nan"))
+    db = torch.full_like(conv.bias, float("nan"))
+    eng._wgrad(L, src, dz, dw, db)
+    dsrc = eng._dgrad(L, dz, None)
+    din = torch.empty(n, hw, hw, cin, device=cuda_dev, dtype=torch.bfloat16)
+    assert eng.lib.esrp_s2d_pad_bwd_nhwc_bf16(dsrc.data_ptr(), din.data_ptr(), None, n, hw, hw, cin,
+                                              torch.cuda.current_stream().cuda_stream) == 0
+    torch.backends.cudnn.allow_tf32 = False
+    xr = act.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    wr = conv.weight.detach().to(torch.bfloat16).float().requires_grad_(True)
+    br = conv.bias.detach().clone().requires_grad_(True)
+    y = F.conv2d(xr, wr, br, stride=2, padding=1)
+    y.backward(dz[:, :hw // 2, :hw // 2].float().permute(0, 3, 1, 2).contiguous())
+    assert torch.isfinite(dw).all() and torch.isfinite(db).all()
+    assert (dw - wr.grad).abs().max().item() <= 2e-3 * max(1.0, wr.grad.abs().max().item())
+    assert (db - br.grad).abs().max().item() <= 2e-3 * max(1.0, br.grad.abs().max().item())
+    got = din.float().permute(0, 3, 1, 2)
+    assert (got - xr.grad).abs().max().item() <= 1e-2 * max(1.0, xr.grad.abs().max().item())

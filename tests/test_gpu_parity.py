@@ -357,5 +357,5 @@ def test_discriminator_forward_matches_reference_fixture(cuda_dev, golden_dir):
             close(v, g["after." + k], k, 2e-2)
         elif "num_batches" in k:
             assert int(v) == int(g["after." + k])
-    with pytest.raises(NotImplementedError):
-        d(x.requires_grad_(True))
+    yg = d(x.clone().requires_grad_(True))          # gradient-requiring forward: same numbers, autograd node attached
+    assert yg.requires_grad and yg.grad_fn is not None
