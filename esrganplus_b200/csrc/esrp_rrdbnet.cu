@@ -162,6 +162,7 @@ void esrp_rrdbnet_destroy(esrp_rrdbnet_t* h) {
   Rrdbnet* m = reinterpret_cast<Rrdbnet*>(h);
   if (!m) return;
   destroy_train_state(m);
+  if (m->pack_jobs_dev) cudaFree(m->pack_jobs_dev);
   if (m->wbuf) cudaFree(m->wbuf);
   delete m;
 }
@@ -192,8 +193,29 @@ int esrp_rrdbnet_load_weights(esrp_rrdbnet_t* h, const void* const* ptrs, int32_
     if (!ptrs[i]) return set_error("rrdbnet_load_weights: tensor %d (%s) is null", i, m->keys[i].c_str());
   m->src_ptrs.assign(ptrs, ptrs + count);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // keep each conv in the layout its last plan asked for (ROW until a plan says otherwise)
-  if (for_each_conv(m, [&](ConvW* c) { return pack_one(m, c, c->layout < 0 ? ESRP_LAYOUT_ROW : c->layout, s); })) return 1;
+  // keep each conv in the layout its last plan asked for (ROW until a plan says otherwise); one batched launch
+  m->pack_jobs_host.clear();
+  for_each_conv(m, [&](ConvW* c) {
+    if (c->layout < 0) c->layout = ESRP_LAYOUT_ROW;
+    PackJob j;
+    memset(&j, 0, sizeof(j));
+    j.type = 0; j.layout = c->layout; j.row0 = c->row0; j.rows = c->rows; j.kc = c->kc; j.bn = c->bn;
+    j.num_chunks = c->num_chunks;
+    j.out = reinterpret_cast<__nv_bfloat16*>(m->wbuf + c->w_off);
+    j.w = static_cast<const float*>(ptrs[c->w_idx]);
+    j.w_o = c->cout; j.w_i = c->cin;
+    for (int i = 0; i < c->num_chunks; ++i) j.lc0[i] = c->lc0[i];
+    j.aux = c->aux_idx >= 0 ? static_cast<const float*>(ptrs[c->aux_idx]) : nullptr;
+    j.aux_cin = m->nf; j.aux_chunks = c->aux_chunks;
+    j.bias_src = static_cast<const float*>(ptrs[c->b_idx]);
+    j.bias_dst = reinterpret_cast<float*>(m->wbuf + c->b_off);
+    m->pack_jobs_host.push_back(j);
+    return 0;
+  });
+  if (!m->pack_jobs_dev) ESRP_CUDA_OK(cudaMalloc(&m->pack_jobs_dev, sizeof(PackJob) * m->pack_jobs_host.size()));
+  ESRP_CUDA_OK(cudaMemcpyAsync(m->pack_jobs_dev, m->pack_jobs_host.data(), sizeof(PackJob) * m->pack_jobs_host.size(),
+                               cudaMemcpyHostToDevice, s));
+  if (run_pack_batch(m->pack_jobs_dev, static_cast<int>(m->pack_jobs_host.size()), s)) return 1;
   m->weights_loaded = true;
   ++m->weights_version;
   return 0;

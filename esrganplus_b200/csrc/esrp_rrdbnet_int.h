@@ -10,6 +10,7 @@
 
 #include "../../include/esrp.h"
 #include "esrp_host.h"
+#include "esrp_pack.h"
 
 namespace esrp {
 
@@ -59,6 +60,8 @@ struct Rrdbnet {
   bool g_zeroed = false;
   std::vector<Step> steps;
   TrainState* train = nullptr;        // training plan + dgrad weight cache (lazily created)
+  PackJob* pack_jobs_dev = nullptr;   // job table of the batched forward-weight repack (one entry per ConvW)
+  std::vector<PackJob> pack_jobs_host;
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

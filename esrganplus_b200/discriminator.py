@@ -68,6 +68,7 @@ class _Layer:
         self.packed: Dict[Tuple[int, int, int], torch.Tensor] = {}   # (layout, slice, kgroup) -> packed weights
         self.packed_t: Dict[Tuple[int, int], torch.Tensor] = {}      # (layout, input-channel slice) -> dgrad weights
         self.wg_tab = None                                           # cached wgrad unit / scatter tables
+        self.desc: Dict[tuple, object] = {}                          # cached launch descriptors (pointers patched per call)
         self.bias_pad: Optional[torch.Tensor] = None
         self.w3: Optional[torch.Tensor] = None
         self.sig = None
@@ -108,6 +109,7 @@ class DiscriminatorEngine:
             L.bias_pad = torch.zeros(L.cout, device=self.device) if b is None else b.detach().clone()
         L.packed.clear()
         L.packed_t.clear()
+        L.desc.clear()
         L.sig = sig
 
     def _packed(self, L: _Layer, layout: int, s: int, g: int, chunks: List[int]) -> torch.Tensor:
@@ -142,17 +144,29 @@ class DiscriminatorEngine:
             for g, chs in enumerate(groups):
                 last = g == len(groups) - 1
                 lc0 = [ch * L.kc for ch in chs]
-                call = K.ConvCall(n=n, h=gh, w=gw, srcs=[src], kc=L.kc, chunks=[(0, c0) for c0 in lc0], bn=SLICE,
-                                  cout=SLICE, w_packed=self._packed(L, layout, s, g, lc0), w_layout=layout,
-                                  bias=L.bias_pad[s * SLICE:(s + 1) * SLICE] if last else None,
-                                  act=1 if fused else 0)
+                # descriptors are cached per (shape, slice, K group); only the activation pointers change per call
+                key = ("f", n, gh, gw, s, g, fused)
+                d = L.desc.get(key)
+                if d is None:
+                    call = K.ConvCall(n=n, h=gh, w=gw, srcs=[src], kc=L.kc, chunks=[(0, c0) for c0 in lc0], bn=SLICE,
+                                      cout=SLICE, w_packed=self._packed(L, layout, s, g, lc0), w_layout=layout,
+                                      bias=L.bias_pad[s * SLICE:(s + 1) * SLICE] if last else None,
+                                      act=1 if fused else 0)
+                    if fused:
+                        call.out_bf16, call.ob_c0 = out_b, s * SLICE
+                    else:
+                        call.out_f32, call.of_c0 = out_f, s * SLICE
+                        if g > 0:
+                            call.r1, call.r1_c0, call.s1 = out_f, s * SLICE, 1.0
+                    d = L.desc[key] = call.desc()
+                d.src[0] = src.data_ptr()
                 if fused:
-                    call.out_bf16, call.ob_c0 = out_b, s * SLICE
+                    d.out_bf16 = out_b.data_ptr()
                 else:
-                    call.out_f32, call.of_c0 = out_f, s * SLICE
+                    d.out_f32 = out_f.data_ptr()
                     if g > 0:
-                        call.r1, call.r1_c0, call.s1 = out_f, s * SLICE, 1.0
-                call.launch()
+                        d.r1 = out_f.data_ptr()
+                _lib.check(self.lib.esrp_conv3x3_nhwc(C.byref(d), _stream()), "esrp_conv3x3_nhwc")
         return (out_b if fused else out_f), hv, wv
 
     # -- forward ---------------------------------------------------------------------------------
@@ -303,9 +317,17 @@ class DiscriminatorEngine:
                        out_nchw=out_nchw).launch()
             return None
         out = torch.empty((n, gh, gw, L.cin_eff), dtype=torch.bfloat16, device=self.device)
+        st = _stream()
         for s in range(L.cin_eff // SLICE):
-            K.ConvCall(n=n, h=gh, w=gw, srcs=[dz], kc=kc, chunks=chunks, bn=SLICE, cout=SLICE,
-                       w_packed=self._dgrad_packed(L, layout, s, kc), w_layout=layout, out_bf16=out, ob_c0=s * SLICE).launch()
+            key = ("b", n, gh, gw, s)
+            d = L.desc.get(key)
+            if d is None:
+                d = L.desc[key] = K.ConvCall(n=n, h=gh, w=gw, srcs=[dz], kc=kc, chunks=chunks, bn=SLICE, cout=SLICE,
+                                             w_packed=self._dgrad_packed(L, layout, s, kc), w_layout=layout, out_bf16=out,
+                                             ob_c0=s * SLICE).desc()
+            d.src[0] = dz.data_ptr()
+            d.out_bf16 = out.data_ptr()
+            _lib.check(self.lib.esrp_conv3x3_nhwc(C.byref(d), st), "esrp_conv3x3_nhwc")
         return out
 
     def backward(self, module: nn.Module, saved: list, dout: torch.Tensor, need_dx: bool, need_params: bool):

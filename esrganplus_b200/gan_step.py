@@ -1,0 +1,67 @@
+"""The caller of the hot path in training: one relativistic-average GAN step, restating
+``SRRaGANModel.optimize_parameters`` (codes/models/SRRaGAN_model.py:113-186) for the ESRGAN+ recipe without the
+perceptual branch (gan_type 'vanilla' = BCEWithLogits, models/modules/loss.py:5-38; L1 pixel loss :31-39; two Adam
+optimisers :82-89).  The reference's own solver runs unchanged on the drop-in classes; this
+restatement exists so that bench.py and the tests can drive the step on a box that has no copy of the reference.
+
+The O(batch) scalar work (losses on [B,1] logits, Adam) stays in torch; everything that touches an image-sized
+tensor is the native generator / discriminator forward and backward.  With ``data_parallel`` modules the two
+backward passes all-reduce their flat gradient buffers — nothing else is exchanged.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+
+class GanTrainStep:
+    def __init__(self, netG, netD, lr_G: float = 1e-4, lr_D: float = 1e-4, beta1_G: float = 0.9, beta1_D: float = 0.9,
+                 pixel_weight: float = 1e-2, gan_weight: float = 5e-3, weight_decay_G: float = 0.0,
+                 weight_decay_D: float = 0.0):
+        self.netG, self.netD = netG, netD
+        self.l_pix_w, self.l_gan_w = pixel_weight, gan_weight
+        # SRRaGAN_model.py:77-89; fused=True is the same Adam arithmetic as one multi-tensor kernel (771 + 69 tensors)
+        fused = all(p.is_cuda for p in netG.parameters())
+        self.optimizer_G = torch.optim.Adam([p for p in netG.parameters() if p.requires_grad], lr=lr_G,
+                                            weight_decay=weight_decay_G, betas=(beta1_G, 0.999), fused=fused)
+        self.optimizer_D = torch.optim.Adam(netD.parameters(), lr=lr_D, weight_decay=weight_decay_D, betas=(beta1_D, 0.999),
+                                            fused=fused)
+        self.log: Dict[str, torch.Tensor] = {}
+        self.fake_H: Optional[torch.Tensor] = None
+
+    @staticmethod
+    def _gan(pred: torch.Tensor, target_is_real: bool) -> torch.Tensor:
+        """GANLoss('vanilla', 1.0, 0.0) (loss.py:11-38): BCEWithLogits against a constant label."""
+        return F.binary_cross_entropy_with_logits(pred, torch.full_like(pred, 1.0 if target_is_real else 0.0))
+
+    def step(self, var_L: torch.Tensor, var_H: torch.Tensor, var_ref: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        var_ref = var_H if var_ref is None else var_ref
+        netG, netD = self.netG, self.netD
+        # ---- G (SRRaGAN_model.py:115-141): D frozen, its data gradient flows into G
+        for p in netD.parameters():
+            p.requires_grad = False
+        self.optimizer_G.zero_grad()
+        self.fake_H = netG(var_L)
+        l_g_pix = self.l_pix_w * F.l1_loss(self.fake_H, var_H)
+        pred_g_fake = netD(self.fake_H)
+        pred_d_real = netD(var_ref).detach()
+        l_g_gan = self.l_gan_w * (self._gan(pred_d_real - torch.mean(pred_g_fake), False) +
+                                  self._gan(pred_g_fake - torch.mean(pred_d_real), True)) / 2
+        (l_g_pix + l_g_gan).backward()
+        self.optimizer_G.step()
+        # ---- D (SRRaGAN_model.py:143-168)
+        for p in netD.parameters():
+            p.requires_grad = True
+        self.optimizer_D.zero_grad()
+        pred_d_real = netD(var_ref)
+        pred_d_fake = netD(self.fake_H.detach())
+        l_d_real = self._gan(pred_d_real - torch.mean(pred_d_fake), True)
+        l_d_fake = self._gan(pred_d_fake - torch.mean(pred_d_real), False)
+        ((l_d_real + l_d_fake) / 2).backward()
+        self.optimizer_D.step()
+        # the reference calls .item() on each of these (six host syncs per step, :171-186); kept as device scalars here
+        self.log = {"l_g_pix": l_g_pix.detach(), "l_g_gan": l_g_gan.detach(), "l_d_real": l_d_real.detach(),
+                    "l_d_fake": l_d_fake.detach(), "D_real": pred_d_real.detach().mean(), "D_fake": pred_d_fake.detach().mean()}
+        return self.log
