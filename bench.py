@@ -12,6 +12,8 @@ Inference shards independent tiles across ranks with no collective (weak scaling
              H2D -> RRDBNet.forward -> D2H of the fp32 output image, all inside the timed region.
 `roofline`   the conv3x3 tcgen05 kernel family = every launch of the step but three small
              layout kernels; achieved = algorithmic FLOPs of the step / event time of the step.
+`train`      secondary leg, BASELINE.json config 4: ESRGAN+ GAN train step imgs/s (global batch 32 split across
+             ranks, gradient all-reduce over NCCL); see train_leg().
 `cpu_baseline` / --impl reference: the reference's algorithm (CPU oracle = torch CPU fp32 ops, the
              same ATen kernels the reference's nn.Conv2d dispatches to) on this box's host cores, on
              a bounded sample (one 128x128 tile per step).
@@ -120,6 +122,66 @@ def main_reference(args):
     }))
 
 
+def train_leg(torch, dev, world, rank, dist, steps=8, warmup=3, global_batch=32):
+    """BASELINE.json config 4: one ESRGAN+ GAN step (RRDBNet nb=23 nf=64 G + Discriminator_VGG_128 D, no perceptual,
+    SRRaGAN_model.py:113-186) on 128x128 HR / 32x32 LR synthetic crops; the global batch of 32 is split across ranks
+    (strong scaling) and the two backward passes all-reduce their flat gradient buffers over NCCL.  imgs/s from CUDA
+    events, max over ranks."""
+    import esrganplus_b200 as E
+    from esrganplus_b200.autograd import broadcast_parameters, data_parallel
+    from esrganplus_b200.gan_step import GanTrainStep
+    from oracle import esrgan_oracle as O  # synthetic weights only
+    bs = max(1, global_batch // world)
+    netG = E.RRDBNet(3, 3, NF, NB)
+    sd = O.synth_state_dict_g(3, 3, NF, NB, seed=31)
+    # ~ kaiming x 0.1 with zero bias, what networks.py:103-104 does for G before training
+    netG.load_state_dict({k: v * (0.1 if k.endswith("weight") else 0.0) for k, v in sd.items()}, strict=True)
+    netD = E.Discriminator_VGG_128(3, 64)
+    netD.load_state_dict(O.synth_state_dict_d(3, 64, seed=32), strict=True)
+    netG, netD = netG.to(dev).train(), netD.to(dev).train()
+    if dist is not None:
+        broadcast_parameters(netG)
+        broadcast_parameters(netD)
+        data_parallel(netG)
+        data_parallel(netD)
+    step = GanTrainStep(netG, netD)
+    g = torch.Generator().manual_seed(100 + rank)
+    lr = torch.rand(bs, 3, 32, 32, generator=g).to(dev)
+    hr = torch.rand(bs, 3, 128, 128, generator=g).to(dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step.step(lr, hr)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        step.step(lr, hr)
+    e1.record()
+    host_ms = (time.perf_counter() - t0) * 1e3 / steps
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    finite = bool(torch.isfinite(torch.stack(list(step.log.values()))).all().item())
+    fl, bl = netG._engines[dev].train_launches()
+    return {"metric": "gan_train_imgs_per_sec", "value": bs * world * steps / (ms * 1e-3), "unit": "imgs/s",
+            "ms_per_step": ms / steps, "host_issue_ms_per_step": host_ms, "steps": steps, "warmup": warmup,
+            "global_batch": bs * world, "batch_per_gpu": bs, "scaling": "strong", "losses_finite": finite,
+            "workload": "ESRGAN+ GAN step, RRDBNet nb=23 nf=64 + Discriminator_VGG_128, 128x128 HR crops, no perceptual (config 4)",
+            "collective": None if dist is None else "all-reduce(avg) of the flat G (67.4 MB) and D (58.0 MB) gradient buffers, NCCL",
+            "generator_launches_fwd_bwd": [fl, bl],
+            "flops_per_img_algorithmic": 151e9,
+            "achieved_tflops_per_gpu": 151e9 * bs * steps / (ms * 1e-3) / 1e12}
+
+
 def main_ours(args):
     import torch
     import esrganplus_b200 as E
@@ -189,6 +251,12 @@ def main_ours(args):
         for _ in range(2):
             step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
+    train = None
+    if not args.no_train:
+        try:
+            train = train_leg(torch, dev, world, rank, dist)
+        except Exception as e:  # the headline line must survive a failure of the secondary leg
+            train = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     eng = net._engines[dev]
     launches = eng.num_launches
@@ -234,6 +302,7 @@ def main_ours(args):
                          "flops_per_step_per_gpu": flops_step},
             "cpu_baseline": cpu,
             "clocks": clocks,
+            "train": train,
         }
         print(json.dumps(line))
     if dist is not None:
@@ -246,6 +315,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary GAN-train-step leg (config 4)")
     args = ap.parse_args()
     if args.impl == "reference":
         main_reference(args)

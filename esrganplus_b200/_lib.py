@@ -127,6 +127,10 @@ SYMBOLS = {
                                      C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "esrp_bn_bwd_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "esrp_bn_finalize": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int32,
+                                   C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "esrp_bn_bwd_finalize": (C.c_int, [C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
     "esrp_s2d_pad_bwd_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                              C.c_void_p]),
     "esrp_linear_bwd_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

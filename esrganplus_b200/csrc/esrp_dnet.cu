@@ -354,3 +354,81 @@ int esrp_linear_bwd_f32(const float* dy, const float* yout_act, const float* x, 
 }
 
 }  // extern "C"
+
+// -------------------------------------------------------------------------------------------------
+// BatchNorm2d bookkeeping on [C]-sized vectors, one launch each (instead of a dozen framework ops per layer):
+// -------------------------------------------------------------------------------------------------
+namespace esrp {
+
+// sums2c = (sum, sum of squares) over `count` samples per channel (esrp_bn_stats_nhwc_f32).
+// training != 0: batch statistics (biased variance for the normalisation, unbiased for running_var,
+//                torch.nn.BatchNorm2d semantics, block.py:32) + running-stat update with `momentum`;
+// training == 0: running statistics.  coef7c rows 0..4 <- mean, rstd, scale, shift, g_rs (rows 5, 6 zeroed).
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, int training,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var, int c,
+                                   float* __restrict__ coef) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  double mean, var;
+  if (training) {
+    mean = sums[ch] / count;
+    var = sums[c + ch] / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    if (running_mean != nullptr) {
+      running_mean[ch] = static_cast<float>((1.0 - momentum) * running_mean[ch] + momentum * mean);
+      const double unbiased = var * (count / (count > 1.0 ? count - 1.0 : 1.0));
+      running_var[ch] = static_cast<float>((1.0 - momentum) * running_var[ch] + momentum * unbiased);
+    }
+  } else {
+    mean = running_mean[ch];
+    var = running_var[ch];
+  }
+  const double rstd = rsqrt(var + static_cast<double>(eps));
+  const double g = gamma ? gamma[ch] : 1.0, b = beta ? beta[ch] : 0.0;
+  coef[ch] = static_cast<float>(mean);
+  coef[c + ch] = static_cast<float>(rstd);
+  coef[2 * c + ch] = static_cast<float>(g * rstd);
+  coef[3 * c + ch] = static_cast<float>(b - mean * g * rstd);
+  coef[4 * c + ch] = static_cast<float>(g * rstd);
+  coef[5 * c + ch] = 0.f;
+  coef[6 * c + ch] = 0.f;
+}
+
+// After esrp_bn_bwd_reduce: d_gamma = sum dzb*xhat, d_beta = sum dzb; batch-statistics layers also get the
+// a = sum dzb / N, b = sum dzb*xhat / N rows of coef7c that the apply pass subtracts.
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double count, int batch_stats, int c,
+                                       float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  if (batch_stats) {
+    coef[5 * c + ch] = static_cast<float>(sums[ch] / count);
+    coef[6 * c + ch] = static_cast<float>(sums[c + ch] / count);
+  }
+  if (dgamma) dgamma[ch] = static_cast<float>(sums[c + ch]);
+  if (dbeta) dbeta[ch] = static_cast<float>(sums[ch]);
+}
+
+}  // namespace esrp
+
+extern "C" {
+
+int esrp_bn_finalize(const double* sums2c, double count, const float* gamma, const float* beta, float eps, float momentum,
+                     int32_t training, float* running_mean, float* running_var, int32_t c, float* coef7c, void* stream) {
+  if (!coef7c || (training && !sums2c) || (!training && (!running_mean || !running_var))) return esrp::set_error("bn_finalize: bad arguments");
+  esrp::bn_finalize_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      sums2c, count, gamma, beta, eps, momentum, training, running_mean, running_var, c, coef7c);
+  ESRP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int esrp_bn_bwd_finalize(const double* sums2c, double count, int32_t batch_stats, int32_t c, float* coef7c, float* dgamma,
+                         float* dbeta, void* stream) {
+  if (!sums2c || !coef7c) return esrp::set_error("bn_bwd_finalize: bad arguments");
+  esrp::bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sums2c, count, batch_stats, c,
+                                                                                                coef7c, dgamma, dbeta);
+  ESRP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

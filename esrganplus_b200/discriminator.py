@@ -112,13 +112,21 @@ class DiscriminatorEngine:
         L.desc.clear()
         L.sig = sig
 
-    def _packed(self, L: _Layer, layout: int, s: int, g: int, chunks: List[int]) -> torch.Tensor:
-        key = (layout, s, g)
+    def _packed(self, L: _Layer, layout: int, s: int, g: int, chunks: List[int], sl: int = SLICE) -> torch.Tensor:
+        key = (layout, s, g, sl)
         t = L.packed.get(key)
         if t is None:
-            t = K.pack_conv3x3_weights(L.w3, L.kc, SLICE, chunks, row0=s * SLICE, rows=SLICE, layout=layout)
+            t = K.pack_conv3x3_weights(L.w3, L.kc, sl, chunks, row0=s * sl, rows=sl, layout=layout)
             L.packed[key] = t
         return t
+
+    @staticmethod
+    def _slice_width(channels: int, layout: int, chunks_per_launch: int) -> int:
+        """Output channels per launch: 64 (UMMA N = 192) where the kernel family allows it — the tile kernel streams
+        its weights, the row kernel keeps them resident and only fits one 64-wide chunk — else 32."""
+        if channels % 64 == 0 and (layout == _lib.LAYOUT_TILE or chunks_per_launch == 1):
+            return 64
+        return 32
 
     # -- one conv layer: NHWC bf16 [n,h,w,cin_pad] -> fp32 NHWC on the conv grid (or bf16 when fused) ------
     def _conv(self, L: _Layer, act: torch.Tensor, fuse_act_bf16: bool, keep: Optional[list] = None):
@@ -140,6 +148,7 @@ class DiscriminatorEngine:
         fused = fuse_act_bf16 and len(groups) == 1
         out_f = None if fused else torch.empty((n, gh, gw, L.cout), dtype=torch.float32, device=self.device)
         out_b = torch.empty((n, gh, gw, L.cout), dtype=torch.bfloat16, device=self.device) if fused else None
+        SLICE = self._slice_width(L.cout, layout, max(len(g_) for g_ in groups))
         for s in range(L.cout // SLICE):
             for g, chs in enumerate(groups):
                 last = g == len(groups) - 1
@@ -149,7 +158,7 @@ class DiscriminatorEngine:
                 d = L.desc.get(key)
                 if d is None:
                     call = K.ConvCall(n=n, h=gh, w=gw, srcs=[src], kc=L.kc, chunks=[(0, c0) for c0 in lc0], bn=SLICE,
-                                      cout=SLICE, w_packed=self._packed(L, layout, s, g, lc0), w_layout=layout,
+                                      cout=SLICE, w_packed=self._packed(L, layout, s, g, lc0, SLICE), w_layout=layout,
                                       bias=L.bias_pad[s * SLICE:(s + 1) * SLICE] if last else None,
                                       act=1 if fused else 0)
                     if fused:
@@ -195,27 +204,26 @@ class DiscriminatorEngine:
             gh, gw, c = y.shape[1], y.shape[2], L.cout
             bn = L.bn
             count = n * hv * wv
-            if bn.training:
+            st = _stream()
+            coef = torch.empty((7, c), dtype=torch.float32, device=self.device)
+            batch_stats = bool(bn.training or bn.running_mean is None)
+            sums = None
+            if batch_stats:
                 sums = torch.empty(2 * c, dtype=torch.float64, device=self.device)
-                _lib.check(self.lib.esrp_bn_stats_nhwc_f32(y.data_ptr(), n, hv, wv, gh, gw, c, sums.data_ptr(), _stream()),
-                           "bn_stats")
-                with torch.no_grad():
-                    mean = sums[:c] / count
-                    var = (sums[c:] / count - mean * mean).clamp_min_(0)          # biased (block.py:32 -> nn.BatchNorm2d)
-                    if bn.track_running_stats and bn.running_mean is not None:
-                        m = bn.momentum if bn.momentum is not None else 0.1
-                        bn.running_mean.mul_(1 - m).add_(mean.float(), alpha=m)
-                        bn.running_var.mul_(1 - m).add_((var * (count / max(count - 1, 1))).float(), alpha=m)
-                        bn.num_batches_tracked.add_(1)
-            else:
-                mean, var = bn.running_mean.double(), bn.running_var.double()
-            with torch.no_grad():
-                rstd = torch.rsqrt(var + bn.eps)
-                scale = (bn.weight.detach().double() * rstd).float().contiguous()
-                shift = (bn.bias.detach().double() - mean * bn.weight.detach().double() * rstd).float().contiguous()
-                if rec is not None:
-                    rec.update(y=y, mean=mean.float(), rstd=rstd.float(), scale=scale, shift=shift, count=count,
-                               batch_stats=bool(bn.training))
+                _lib.check(self.lib.esrp_bn_stats_nhwc_f32(y.data_ptr(), n, hv, wv, gh, gw, c, sums.data_ptr(), st), "bn_stats")
+            track = batch_stats and bn.track_running_stats and bn.running_mean is not None
+            m = bn.momentum if bn.momentum is not None else 0.1
+            _lib.check(self.lib.esrp_bn_finalize(sums.data_ptr() if sums is not None else None, float(count),
+                                                 bn.weight.data_ptr() if bn.weight is not None else None,
+                                                 bn.bias.data_ptr() if bn.bias is not None else None, float(bn.eps), float(m),
+                                                 int(batch_stats), bn.running_mean.data_ptr() if (track or not batch_stats) else None,
+                                                 bn.running_var.data_ptr() if (track or not batch_stats) else None, c,
+                                                 coef.data_ptr(), st), "bn_finalize")
+            if track:
+                bn.num_batches_tracked.add_(1)
+            scale, shift = coef[2], coef[3]
+            if rec is not None:
+                rec.update(y=y, coef=coef, count=count, batch_stats=batch_stats)
             nxt = torch.empty((n, hv, wv, c), dtype=torch.bfloat16, device=self.device)
             if is_last:
                 flat = torch.empty((n, c * hv * wv), dtype=torch.float32, device=self.device)
@@ -234,12 +242,12 @@ class DiscriminatorEngine:
         return out
 
     # -- backward --------------------------------------------------------------------------------
-    def _dgrad_packed(self, L: _Layer, layout: int, s: int, kc: int) -> torch.Tensor:
-        key = (layout, s)
+    def _dgrad_packed(self, L: _Layer, layout: int, s: int, kc: int, sl: int = SLICE) -> torch.Tensor:
+        key = (layout, s, sl)
         t = L.packed_t.get(key)
         if t is None:
             groups = [(L.w3, 32 * g, 1.0) for g in range(L.cout // 32)]
-            t = K.pack_dgrad_weights(groups, s * SLICE, min(SLICE, L.cin_eff - s * SLICE), kc, SLICE, layout=layout)
+            t = K.pack_dgrad_weights(groups, s * sl, min(sl, L.cin_eff - s * sl), kc, sl, layout=layout)
             L.packed_t[key] = t
         return t
 
@@ -308,22 +316,23 @@ class DiscriminatorEngine:
             raise NotImplementedError("Discriminator_VGG_128 backward: K does not fit one launch for this layer width")
         chunks = [(0, c * kc) for c in range(nchunks)]
         if out_nchw is not None:
-            wp = L.packed_t.get((layout, -1))
+            wp = L.packed_t.get((layout, -1, 16))
             if wp is None:
                 groups = [(L.w3, 32 * g, 1.0) for g in range(L.cout // 32)]
                 wp = K.pack_dgrad_weights(groups, 0, L.cin, kc, 16, layout=layout)
-                L.packed_t[(layout, -1)] = wp
+                L.packed_t[(layout, -1, 16)] = wp
             K.ConvCall(n=n, h=gh, w=gw, srcs=[dz], kc=kc, chunks=chunks, bn=16, cout=L.cin, w_packed=wp, w_layout=layout,
                        out_nchw=out_nchw).launch()
             return None
         out = torch.empty((n, gh, gw, L.cin_eff), dtype=torch.bfloat16, device=self.device)
         st = _stream()
+        SLICE = self._slice_width(L.cin_eff, layout, nchunks)
         for s in range(L.cin_eff // SLICE):
             key = ("b", n, gh, gw, s)
             d = L.desc.get(key)
             if d is None:
                 d = L.desc[key] = K.ConvCall(n=n, h=gh, w=gw, srcs=[dz], kc=kc, chunks=chunks, bn=SLICE, cout=SLICE,
-                                             w_packed=self._dgrad_packed(L, layout, s, kc), w_layout=layout, out_bf16=out,
+                                             w_packed=self._dgrad_packed(L, layout, s, kc, SLICE), w_layout=layout, out_bf16=out,
                                              ob_c0=s * SLICE).desc()
             d.src[0] = dz.data_ptr()
             d.out_bf16 = out.data_ptr()
@@ -369,20 +378,14 @@ class DiscriminatorEngine:
                 y = rec["y"]
                 gh, gw = y.shape[1], y.shape[2]
                 bi = idx_of[id(L.bn)]
-                gamma = L.bn.weight.detach()
-                coef = torch.zeros((7, c), dtype=torch.float32, device=self.device)
-                coef[0], coef[1], coef[2], coef[3] = rec["mean"], rec["rstd"], rec["scale"], rec["shift"]
-                coef[4] = gamma * rec["rstd"]
+                coef = rec["coef"]
                 sums = torch.empty(2 * c, dtype=torch.float64, device=self.device)
                 db_, dn_ = (dout_b.data_ptr() if dout_b is not None else None), (dout_nchw.data_ptr() if dout_nchw is not None else None)
                 _lib.check(self.lib.esrp_bn_bwd_reduce(y.data_ptr(), db_, dn_, n, hv, wv, gh, gw, c, coef.data_ptr(),
                                                        sums.data_ptr(), st), "bn_bwd_reduce")
-                if rec["batch_stats"]:
-                    coef[5] = (sums[:c] / rec["count"]).float()
-                    coef[6] = (sums[c:] / rec["count"]).float()
-                if need_params:
-                    grads[f"features.{bi}.weight"].copy_(sums[c:])
-                    grads[f"features.{bi}.bias"].copy_(sums[:c])
+                _lib.check(self.lib.esrp_bn_bwd_finalize(sums.data_ptr(), float(rec["count"]), int(rec["batch_stats"]), c,
+                                                         coef.data_ptr(), gp(f"features.{bi}.weight"), gp(f"features.{bi}.bias"), st),
+                           "bn_bwd_finalize")
                 dz = torch.empty((n, gh, gw, c), dtype=torch.bfloat16, device=self.device)
                 _lib.check(self.lib.esrp_bn_bwd_apply(y.data_ptr(), db_, dn_, n, hv, wv, gh, gw, c, coef.data_ptr(),
                                                       dz.data_ptr(), st), "bn_bwd_apply")

@@ -182,6 +182,16 @@ int esrp_bn_bwd_reduce(const float* z, const void* dout_bf16, const float* dout_
                        int32_t hp, int32_t wp, int32_t c, const float* coef7c, double* sums2c, void* stream);
 int esrp_bn_bwd_apply(const float* z, const void* dout_bf16, const float* dout_nchw_f32, int32_t n, int32_t h, int32_t w,
                       int32_t hp, int32_t wp, int32_t c, const float* coef7c, void* dz_bf16, void* stream);
+/* BatchNorm2d bookkeeping on [c]-sized vectors in one launch.  esrp_bn_finalize: from the sums of
+ * esrp_bn_stats_nhwc_f32 over `count` samples per channel (training != 0: batch statistics, biased variance for the
+ * normalisation and the momentum update of running_mean / running_var with the unbiased variance — nn.BatchNorm2d
+ * semantics, block.py:32; training == 0: the running statistics) to coef7c rows mean, rstd, scale, shift, g_rs
+ * (rows a, b zeroed).  esrp_bn_bwd_finalize: from the sums of esrp_bn_bwd_reduce to d_gamma / d_beta and, for
+ * batch-statistics layers, the a / b rows. */
+int esrp_bn_finalize(const double* sums2c, double count, const float* gamma, const float* beta, float eps, float momentum,
+                     int32_t training, float* running_mean, float* running_var, int32_t c, float* coef7c, void* stream);
+int esrp_bn_bwd_finalize(const double* sums2c, double count, int32_t batch_stats, int32_t c, float* coef7c, float* dgamma,
+                         float* dbeta, void* stream);
 /* Inverse of esrp_s2d_pad_nhwc_bf16 (gradient of the rearrangement): ds [n,h/2+1,w/2+1,4c] -> din [n,h,w,c];
  * lrelu_ref (optional, bf16 [n,h,w,c]): din *= (ref > 0 ? 1 : 0.2), the LeakyReLU derivative of the activation fed forward. */
 int esrp_s2d_pad_bwd_nhwc_bf16(const void* ds, void* din, const void* lrelu_ref, int32_t n, int32_t h, int32_t w, int32_t c,

@@ -148,10 +148,10 @@ def test_generator_backward_train_mode_noise(cuda_dev):
             row.append(torch.from_numpy(buf).reshape(n, h, w, nf).permute(0, 3, 1, 2).contiguous())
         noises.append(row)
     ref_g = _check(net, x, sd, nb, dy, "train-mode noise", training=True, noises=noises, y=y)
-    # the noise must matter: gradients without it differ by more than the tolerance
+    # the noise must matter: the fp32 gradients with and without it differ by > 10 % (measured: 20 %)
     _, g_eval = _oracle_grads(x, sd, nb, dy)
     k = "model.1.sub.0.RDB1.conv1.0.weight"
-    assert (g_eval[k] - ref_g[k]).norm() > 2 * REL_L2 * ref_g[k].norm()
+    assert (g_eval[k] - ref_g[k]).norm() > 0.1 * ref_g[k].norm()
 
 
 def test_generator_backward_frozen_parameters_and_reuse(cuda_dev):

@@ -21,6 +21,7 @@ ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--tile", type=int, default=128)
 ap.add_argument("--nb", type=int, default=23)
 ap.add_argument("--train", action="store_true")
+ap.add_argument("--bwd", action="store_true", help="profile one training forward + backward (parameters require grad)")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 net = E.RRDBNet(3, 3, 64, a.nb)
@@ -30,6 +31,18 @@ net.train(a.train)
 for p in net.parameters():
     p.requires_grad = False
 x = torch.rand(a.batch, 3, a.tile, a.tile, device=dev)
+if a.bwd:
+    for p in net.parameters():
+        p.requires_grad = True
+    dy = torch.randn(a.batch, 3, 4 * a.tile, 4 * a.tile, device=dev)
+    net(x).backward(dy)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    net(x).backward(dy)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    print("done")
+    sys.exit(0)
 with torch.no_grad():
     net(x)
     torch.cuda.synchronize()
