@@ -12,8 +12,8 @@ Inference shards independent tiles across ranks with no collective (weak scaling
              H2D -> RRDBNet.forward -> D2H of the fp32 output image, all inside the timed region.
 `roofline`   the conv3x3 tcgen05 kernel family = every launch of the step but three small
              layout kernels; achieved = algorithmic FLOPs of the step / event time of the step.
-`train`      secondary leg, BASELINE.json config 4: ESRGAN+ GAN train step imgs/s (global batch 32 split across
-             ranks, gradient all-reduce over NCCL); see train_leg().
+`train`      secondary leg, BASELINE.json config 4: ESRGAN+ GAN train step imgs/s, 32 crops per GPU (weak scaling),
+             gradient all-reduce over NCCL; `train_strong` (N > 1 only): the same with 32 crops in total; see train_leg().
 `cpu_baseline` / --impl reference: the reference's algorithm (CPU oracle = torch CPU fp32 ops, the
              same ATen kernels the reference's nn.Conv2d dispatches to) on this box's host cores, on
              a bounded sample (one 128x128 tile per step).
@@ -122,11 +122,12 @@ def main_reference(args):
     }))
 
 
-def train_leg(torch, dev, world, rank, dist, steps=8, warmup=3, global_batch=32):
+def train_leg(torch, dev, world, rank, dist, steps=8, warmup=3, global_batch=32, scaling="strong"):
     """BASELINE.json config 4: one ESRGAN+ GAN step (RRDBNet nb=23 nf=64 G + Discriminator_VGG_128 D, no perceptual,
-    SRRaGAN_model.py:113-186) on 128x128 HR / 32x32 LR synthetic crops; the global batch of 32 is split across ranks
-    (strong scaling) and the two backward passes all-reduce their flat gradient buffers over NCCL.  imgs/s from CUDA
-    events, max over ranks."""
+    SRRaGAN_model.py:113-186) on 128x128 HR / 32x32 LR synthetic crops; `global_batch` is split across ranks and the
+    two backward passes all-reduce their flat gradient buffers over NCCL.  imgs/s from CUDA events, max over ranks.
+    BASELINE.json's "bs=32 ... DDP 8xB200" is read both ways: weak = 32 crops per GPU, strong = 32 in
+    total."""
     import esrganplus_b200 as E
     from esrganplus_b200.autograd import broadcast_parameters, data_parallel
     from esrganplus_b200.gan_step import GanTrainStep
@@ -174,7 +175,7 @@ def train_leg(torch, dev, world, rank, dist, steps=8, warmup=3, global_batch=32)
     fl, bl = netG._engines[dev].train_launches()
     return {"metric": "gan_train_imgs_per_sec", "value": bs * world * steps / (ms * 1e-3), "unit": "imgs/s",
             "ms_per_step": ms / steps, "host_issue_ms_per_step": host_ms, "steps": steps, "warmup": warmup,
-            "global_batch": bs * world, "batch_per_gpu": bs, "scaling": "strong", "losses_finite": finite,
+            "global_batch": bs * world, "batch_per_gpu": bs, "scaling": scaling, "losses_finite": finite,
             "workload": "ESRGAN+ GAN step, RRDBNet nb=23 nf=64 + Discriminator_VGG_128, 128x128 HR crops, no perceptual (config 4)",
             "collective": None if dist is None else "all-reduce(avg) of the flat G (67.4 MB) and D (58.0 MB) gradient buffers, NCCL",
             "generator_launches_fwd_bwd": [fl, bl],
@@ -251,12 +252,14 @@ def main_ours(args):
         for _ in range(2):
             step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
-    train = None
+    train = train_strong = None
     if not args.no_train:
         try:
-            train = train_leg(torch, dev, world, rank, dist)
+            train = train_leg(torch, dev, world, rank, dist, global_batch=32 * world, scaling="weak")
+            if world > 1:
+                train_strong = train_leg(torch, dev, world, rank, dist, global_batch=32, scaling="strong")
         except Exception as e:  # the headline line must survive a failure of the secondary leg
-            train = {"error": f"{type(e).__name__}: {e}"[:300]}
+            train = train or {"error": f"{type(e).__name__}: {e}"[:300]}
 
     eng = net._engines[dev]
     launches = eng.num_launches
@@ -303,6 +306,7 @@ def main_ours(args):
             "cpu_baseline": cpu,
             "clocks": clocks,
             "train": train,
+            "train_strong": train_strong,
         }
         print(json.dumps(line))
     if dist is not None:
