@@ -18,6 +18,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/esrp.h"
@@ -279,78 +280,127 @@ __global__ void wgrad_scatter_kernel(const esrp_scatter_entry_t* __restrict__ ta
 //   g[px][c]  += sum_k dx2[px][k] * U[k][c]  (+ extra[px][c])          data gradient, in place on the fp32 trunk gradient
 //   dU[k][c]  += sum_px dx2[px][k] * x[px][c]                           weight gradient (atomics per CTA)
 // ------------------------------------------------------------------------------------------------
+// Both products run on warp-level bf16 MMAs (mma.sync m16n8k16, fp32 accumulate) from padded shared-memory tiles of 64
+// pixels: O = D . U (A = D row-major via ldmatrix, B = U^T staged once per CTA as bf16 — the forward's packed 1x1 is bf16
+// too) and dU = D^T . X (contraction over pixels, both fragments via ldmatrix.trans like conv3x3_wgrad_kernel).  The
+// kernel is then bound by its HBM traffic (x, dx2 in; the fp32 trunk gradient in and out).
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
 template <int NF>
-__global__ void __launch_bounds__(256) conv1x1_bwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ctotal,
-                                                          const __nv_bfloat16* __restrict__ dx2, int d_ctotal, int d_c0,
-                                                          const float* __restrict__ u, float* __restrict__ g,
-                                                          const float* __restrict__ extra, float* __restrict__ du_acc,
-                                                          long long npx) {
-  constexpr int TP = 64;
-  __shared__ float us[32][NF];
-  __shared__ float xs[TP][NF + 4];
-  __shared__ float ds[TP][33];
-  const int tid = threadIdx.x;
-  for (int i = tid; i < 32 * NF; i += 256) us[i / NF][i % NF] = u[i];
-  constexpr int CPT = 32 * NF / 256;  // dU elements per thread: k = tid / (256/32) ...
-  const int wk = tid >> 3;            // 0..31: dx2 channel
-  const int wc0 = (tid & 7) * CPT;    // first x channel
-  float wacc[CPT];
+__global__ void __launch_bounds__(256, 3) conv1x1_bwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ctotal,
+                                                             const __nv_bfloat16* __restrict__ dx2, int d_ctotal, int d_c0,
+                                                             const float* __restrict__ u, float* __restrict__ g,
+                                                             const float* __restrict__ extra, float* __restrict__ du_acc,
+                                                             long long npx) {
+  constexpr int TP = 64;                 // pixels per tile
+  constexpr int DP = 80;                 // bytes per row of the D tile / of U^T (32 bf16 + 16 pad: conflict-free ldmatrix)
+  constexpr int XP = NF * 2 + 16;        // bytes per row of the X tile
+  constexpr int NT1 = NF / 16;           // n8 tiles per warp in O = D . U   (warp = 16 pixels x NF/2 channels)
+  __shared__ __align__(16) uint8_t ut[NF * DP];
+  __shared__ __align__(16) uint8_t dsm[TP * DP];
+  __shared__ __align__(16) uint8_t xsm[TP * XP];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 32 * NF; i += 256) {
+    const int k = i / NF, c = i % NF;
+    *reinterpret_cast<__nv_bfloat16*>(ut + c * DP + k * 2) = __float2bfloat16_rn(u[i]);
+  }
+  // part 1 (O = D . U): warp -> pixel rows m0 .., channels n0 ..
+  const int m0 = 16 * (warp & 3), n0 = (NF / 2) * (warp >> 2);
+  // part 2 (dU = D^T . X): warp -> dx2 channels 16 * mi .., x channels 16 * nh ..
+  const int mi = warp & 1, nh = warp >> 1;
+  const bool du_warp = du_acc != nullptr && nh * 16 < NF;
+  float du[2][4];
 #pragma unroll
-  for (int i = 0; i < CPT; ++i) wacc[i] = 0.f;
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) du[j][i] = 0.f;
+  const uint32_t ut_a = smem_u32(ut), ds_a = smem_u32(dsm), xs_a = smem_u32(xsm);
   const long long ntiles = (npx + TP - 1) / TP;
   for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const long long p0 = t * TP;
     __syncthreads();
-    for (int i = tid; i < TP * NF; i += 256) {
-      const int px = i / NF, c = i % NF;
-      xs[px][c] = (p0 + px < npx) ? __bfloat162float(x[(p0 + px) * x_ctotal + c]) : 0.f;
+    for (int i = tid; i < TP * 4; i += 256) {
+      const int seg = i & 3, px = i >> 2;
+      const bool ok = p0 + px < npx;
+      cp_async16_zfill(ds_a + px * DP + seg * 16, dx2 + (ok ? p0 + px : 0) * d_ctotal + d_c0 + seg * 8, ok);
     }
-    for (int i = tid; i < TP * 32; i += 256) {
-      const int px = i >> 5, k = i & 31;
-      ds[px][k] = (p0 + px < npx) ? __bfloat162float(dx2[(p0 + px) * d_ctotal + d_c0 + k]) : 0.f;
+    for (int i = tid; i < TP * (NF / 8); i += 256) {
+      const int seg = i % (NF / 8), px = i / (NF / 8);
+      const bool ok = p0 + px < npx;
+      cp_async16_zfill(xs_a + px * XP + seg * 16, x + (ok ? p0 + px : 0) * x_ctotal + seg * 8, ok);
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
-    // data gradient: thread -> pixel tid / 4, channels (tid % 4) * NF/4 ..
+    // ---- data gradient: g[px][c] += sum_k D[px][k] U[k][c] (+ extra)
     {
-      constexpr int CQ = NF / 4;
-      const int px = tid >> 2, c0 = (tid & 3) * CQ;
-      if (p0 + px < npx) {
-        float o[CQ];
+      float o[NT1][4];
 #pragma unroll
-        for (int i = 0; i < CQ; ++i) o[i] = 0.f;
-#pragma unroll 4
-        for (int k = 0; k < 32; ++k) {
-          const float d = ds[px][k];
+      for (int j = 0; j < NT1; ++j)
 #pragma unroll
-          for (int i = 0; i < CQ; ++i) o[i] = fmaf(d, us[k][c0 + i], o[i]);
+        for (int i = 0; i < 4; ++i) o[j][i] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        uint32_t a[4];
+        ldmatrix_x4(ds_a + (m0 + (lane & 15)) * DP + (kk * 16 + (lane >> 4) * 8) * 2, a);
+#pragma unroll
+        for (int np = 0; np < NT1 / 2; ++np) {
+          uint32_t b[4];
+          ldmatrix_x4(ut_a + (n0 + np * 16 + (lane & 7) + (lane >> 4) * 8) * DP + (kk * 16 + ((lane >> 3) & 1) * 8) * 2, b);
+          mma_bf16_16816(o[2 * np], a, b[0], b[1]);
+          mma_bf16_16816(o[2 * np + 1], a, b[2], b[3]);
         }
-        float* gp = g + (p0 + px) * NF + c0;
-        const float* ep = extra ? extra + (p0 + px) * NF + c0 : nullptr;
+      }
 #pragma unroll
-        for (int i = 0; i < CQ; i += 4) {
-          float4 v = *reinterpret_cast<float4*>(gp + i);
-          v.x += o[i]; v.y += o[i + 1]; v.z += o[i + 2]; v.w += o[i + 3];
-          if (ep) {
-            const float4 e4 = *reinterpret_cast<const float4*>(ep + i);
-            v.x += e4.x; v.y += e4.y; v.z += e4.z; v.w += e4.w;
+      for (int hrow = 0; hrow < 2; ++hrow) {
+        const long long px = p0 + m0 + (lane >> 2) + hrow * 8;
+        if (px < npx) {
+#pragma unroll
+          for (int j = 0; j < NT1; ++j) {
+            const size_t off = static_cast<size_t>(px) * NF + n0 + j * 8 + (lane & 3) * 2;
+            float2 v = *reinterpret_cast<float2*>(g + off);
+            v.x += o[j][hrow * 2];
+            v.y += o[j][hrow * 2 + 1];
+            if (extra != nullptr) {
+              const float2 e2 = *reinterpret_cast<const float2*>(extra + off);
+              v.x += e2.x;
+              v.y += e2.y;
+            }
+            *reinterpret_cast<float2*>(g + off) = v;
           }
-          *reinterpret_cast<float4*>(gp + i) = v;
         }
       }
     }
-    // weight gradient
-    if (du_acc != nullptr) {
-#pragma unroll 4
-      for (int px = 0; px < TP; ++px) {
-        const float d = ds[px][wk];
+    // ---- weight gradient: dU[k][c] += sum_px D[px][k] X[px][c]
+    if (du_warp) {
+      const int a_px = (lane & 7) + ((lane >> 4) << 3);
+      const int a_off = a_px * DP + (mi * 16 + ((lane >> 3) & 1) * 8) * 2;
+      const int b_px = (lane & 7) + (((lane >> 3) & 1) << 3);
+      const int b_off = b_px * XP + (nh * 16 + (lane >> 4) * 8) * 2;
 #pragma unroll
-        for (int i = 0; i < CPT; ++i) wacc[i] = fmaf(d, xs[px][wc0 + i], wacc[i]);
+      for (int ks = 0; ks < TP / 16; ++ks) {
+        uint32_t a[4], b[4];
+        ldmatrix_x4_trans(ds_a + ks * 16 * DP + a_off, a);
+        ldmatrix_x4_trans(xs_a + ks * 16 * XP + b_off, b);
+        mma_bf16_16816(du[0], a, b[0], b[1]);
+        mma_bf16_16816(du[1], a, b[2], b[3]);
       }
     }
   }
-  if (du_acc != nullptr) {
+  if (du_warp) {
+    const int k = mi * 16 + (lane >> 2);
+    const int c = nh * 16 + (lane & 3) * 2;
 #pragma unroll
-    for (int i = 0; i < CPT; ++i) atomicAdd(du_acc + wk * NF + wc0 + i, wacc[i]);
+    for (int j = 0; j < 2; ++j) {
+      atomicAdd(du_acc + k * NF + c + j * 8, du[j][0]);
+      atomicAdd(du_acc + k * NF + c + j * 8 + 1, du[j][1]);
+      atomicAdd(du_acc + (k + 8) * NF + c + j * 8, du[j][2]);
+      atomicAdd(du_acc + (k + 8) * NF + c + j * 8 + 1, du[j][3]);
+    }
   }
 }
 
@@ -413,6 +463,21 @@ __global__ void upsample2x_bwd_kernel(const uint4* __restrict__ dup, int n, int 
 int plan_wgrad(const esrp_wgrad_unit_t* units, int num_units, int n, int h, int w, int splits, WgradLaunch* out) {
   if (!units || num_units < 1 || num_units > ESRP_WGRAD_MAX_UNITS) return set_error("wgrad: num_units=%d out of range (1..%d)", num_units, ESRP_WGRAD_MAX_UNITS);
   if (n < 1 || h < 1 || w < 1) return set_error("wgrad: bad shape");
+  // default: the tcgen05 kernel (esrp_wgrad_tc.cu); ESRP_WGRAD_MMA=1 or an explicit split count selects the mma.sync
+  // kernel below, which also takes over where a tensor map cannot be encoded for the tcgen05 tiling
+  static const bool force_mma = getenv("ESRP_WGRAD_MMA") != nullptr;
+  if (!force_mma && splits <= 0) {
+    bool ok = true;
+    for (int i = 0; i < num_units; ++i)
+      if (!units[i].x || !units[i].dy || !units[i].acc || (units[i].x_c0 % 32) || (units[i].dy_c0 % 64)) ok = false;
+    static const bool strict = getenv("ESRP_WGRAD_TC_STRICT") != nullptr;  // tests: a refused tcgen05 plan is an error
+    if (ok) {
+      if (plan_wgrad_tc(units, num_units, n, h, w, out) == 0) return 0;
+      if (strict) return 1;
+    }
+  }
+  out->tc = 0;
+  out->num_bias = 0;
   WgradParams& p = *reinterpret_cast<WgradParams*>(out->params);
   static_assert(sizeof(WgradParams) <= sizeof(out->params), "WgradLaunch::params too small");
   memset(&p, 0, sizeof(p));
@@ -454,6 +519,7 @@ int plan_wgrad(const esrp_wgrad_unit_t* units, int num_units, int n, int h, int 
 }
 
 int run_wgrad(const WgradLaunch& L, cudaStream_t stream) {
+  if (L.tc) return run_wgrad_tc(L, stream);
   const WgradParams& p = *reinterpret_cast<const WgradParams*>(L.params);
   conv3x3_wgrad_kernel<<<L.grid, kWgThreads, L.smem, stream>>>(p);
   ESRP_CUDA_OK(cudaGetLastError());
@@ -464,7 +530,7 @@ int run_conv1x1_bwd(int nf, const void* x, int x_ctotal, const void* dx2, int d_
                     float* g, const float* extra, float* du_acc, long long npx, cudaStream_t stream) {
   const int sms = sm_count();
   long long tiles = (npx + 63) / 64;
-  int grid = static_cast<int>(tiles < 2LL * sms ? tiles : 2LL * sms);
+  int grid = static_cast<int>(tiles < 3LL * sms ? tiles : 3LL * sms);
   if (grid < 1) return 0;
   if (nf == 64)
     conv1x1_bwd_kernel<64><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), x_ctotal,

@@ -142,7 +142,7 @@ def test_conv1x1_bwd(cuda_dev, nf):
     du = torch.zeros(32, nf, device=cuda_dev)
     K.conv1x1_bwd(x, dx2, 32, u, gbuf, extra, du)
     d = dx2[..., 32:64].float()
-    want_g = g0 + d @ u + extra
+    want_g = g0 + d @ u.to(torch.bfloat16).float() + extra      # the kernel multiplies by the bf16 U the forward uses
     want_du = d.reshape(-1, 32).t() @ x.float().reshape(-1, nf)
     assert (gbuf - want_g).abs().max().item() <= 1e-4 * max(1.0, want_g.abs().max().item())
     assert (du - want_du).abs().max().item() <= 1e-4 * max(1.0, want_du.abs().max().item())
