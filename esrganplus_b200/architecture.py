@@ -83,8 +83,10 @@ class _GeneratorBase(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("esrganplus_b200.RRDBNet runs on CUDA (sm_100a) only; there is no CPU path "
                                "(use the reference modules for CPU inference)")
-        params: Dict[str, torch.Tensor] = dict(self.named_parameters())
-        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params.values()))
+        from .discriminator import _named_params
+        names, plist = _named_params(self)
+        params: Dict[str, torch.Tensor] = dict(zip(names, plist))
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in plist))
         if needs_grad:
             from .autograd import generator_apply
             return generator_apply(self, x, params)

@@ -426,7 +426,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
 #pragma unroll
             for (int i = 0; i < GC; i += 4) {
               float z[4];
-              philox_normal4(p.seed,
+              philox_normal4(p.seed_ptr ? __ldg(p.seed_ptr) : p.seed,
                              p.offset + (pix * static_cast<unsigned long long>(p.noise_ctotal) + p.noise_c0 + ch0 + i) / 4, z);
 #pragma unroll
               for (int j = 0; j < 4; ++j) v[i + j] = fmaf(z[j] * p.sigma, v[i + j], v[i + j]);

@@ -40,6 +40,7 @@ struct ConvKParams {
   int noise, noise_ctotal, noise_c0;
   float sigma;
   unsigned long long seed, offset;
+  const unsigned long long* seed_ptr;  // when non-null the Philox key is read from device memory (CUDA-graph replays)
   __nv_bfloat16* out_bf16;
   int ob_ctotal, ob_c0;
   float* out_f32;

@@ -9,6 +9,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
+#include <unordered_map>
 
 #include "../../include/esrp.h"
 #include "esrp_philox.cuh"
@@ -276,10 +278,37 @@ int esrp_philox_normal_host(uint64_t seed, uint64_t offset, int64_t count, float
   return 0;
 }
 
+// Planning a launch (argument validation, two cuTensorMapEncodeTiled calls, shared-memory / TMEM budgeting) costs more
+// host time than the launch itself.  A caller that issues the same descriptor again — a training loop whose allocator
+// hands out the same addresses every step — hits this small cache keyed on the descriptor bytes (pointers included).
 int esrp_conv3x3_nhwc(const esrp_conv3x3_t* desc, void* stream) {
   if (!desc) return set_error("esrp_conv3x3_nhwc: null desc");
+  static std::mutex mu;
+  static std::unordered_map<std::string, ConvLaunch>* cache = new std::unordered_map<std::string, ConvLaunch>();
+  esrp_conv3x3_t d = *desc;
+  // Philox key / offset and the debug trace pointer do not influence planning: keep them out of the key
+  const unsigned long long seed = d.seed, offset = d.offset;
+  d.seed = d.offset = 0;
+  if (d.trace != nullptr || d.variant != 0) {
+    ConvLaunch L;
+    if (plan_conv(*desc, &L)) return 1;
+    return run_conv(L, static_cast<cudaStream_t>(stream));
+  }
+  std::string key(reinterpret_cast<const char*>(&d), sizeof(d));
   ConvLaunch L;
-  if (plan_conv(*desc, &L)) return 1;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache->find(key);
+    if (it == cache->end()) {
+      if (plan_conv(d, &L)) return 1;
+      if (cache->size() >= 8192) cache->clear();
+      cache->emplace(std::move(key), L);
+    } else {
+      L = it->second;
+    }
+  }
+  L.params.seed = seed;
+  L.params.offset = offset;
   return run_conv(L, static_cast<cudaStream_t>(stream));
 }
 

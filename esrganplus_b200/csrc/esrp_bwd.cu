@@ -20,6 +20,9 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
 
 #include "../../include/esrp.h"
 #include "esrp_bwd.h"
@@ -582,8 +585,25 @@ int esrp_pack_dgrad_weights(const esrp_dgrad_group_t* groups_host, int32_t num_g
 
 int esrp_conv3x3_wgrad(const esrp_wgrad_unit_t* units_host, int32_t num_units, int32_t n, int32_t h, int32_t w,
                        int32_t splits, void* stream) {
+  // same plan cache as esrp_conv3x3_nhwc: planning encodes two tensor maps per job
+  if (!units_host || num_units < 1 || num_units > ESRP_WGRAD_MAX_UNITS) return set_error("wgrad: num_units=%d out of range (1..%d)", num_units, ESRP_WGRAD_MAX_UNITS);
+  static std::mutex mu;
+  static std::unordered_map<std::string, WgradLaunch>* cache = new std::unordered_map<std::string, WgradLaunch>();
+  std::string key(reinterpret_cast<const char*>(units_host), sizeof(esrp_wgrad_unit_t) * num_units);
+  const int32_t shape[4] = {n, h, w, splits};
+  key.append(reinterpret_cast<const char*>(shape), sizeof(shape));
   WgradLaunch L;
-  if (plan_wgrad(units_host, num_units, n, h, w, splits, &L)) return 1;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache->find(key);
+    if (it == cache->end()) {
+      if (plan_wgrad(units_host, num_units, n, h, w, splits, &L)) return 1;
+      if (cache->size() >= 2048) cache->clear();
+      cache->emplace(std::move(key), L);
+    } else {
+      L = it->second;
+    }
+  }
   return run_wgrad(L, static_cast<cudaStream_t>(stream));
 }
 

@@ -20,7 +20,7 @@ void copy_common(const esrp_conv3x3_t& d, ConvKParams* pp) {
   p.r1 = d.r1; p.r1_is_f32 = d.r1_is_f32; p.r1_ctotal = d.r1_ctotal; p.r1_c0 = d.r1_c0; p.s1 = d.s1;
   p.r2 = d.r2; p.r2_is_f32 = d.r2_is_f32; p.r2_ctotal = d.r2_ctotal; p.r2_c0 = d.r2_c0; p.s2 = d.s2;
   p.noise = d.noise; p.noise_ctotal = d.noise_ctotal; p.noise_c0 = d.noise_c0;
-  p.sigma = d.sigma; p.seed = d.seed; p.offset = d.offset;
+  p.sigma = d.sigma; p.seed = d.seed; p.offset = d.offset; p.seed_ptr = nullptr;
   p.out_bf16 = static_cast<__nv_bfloat16*>(d.out_bf16); p.ob_ctotal = d.ob_ctotal; p.ob_c0 = d.ob_c0;
   p.out_f32 = static_cast<float*>(d.out_f32); p.of_ctotal = d.of_ctotal; p.of_c0 = d.of_c0;
   p.out_nchw = d.out_nchw;

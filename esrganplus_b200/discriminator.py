@@ -41,8 +41,29 @@ SLICE = 32            # output channels per launch
 MAX_CHUNKS = {_lib.LAYOUT_ROW: 3, _lib.LAYOUT_TILE: 8}   # K chunks per launch (weights must fit in smem)
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+_STREAM = [0]
+
+
+def _stream(refresh: bool = False) -> int:
+    """cudaStream_t of torch's current stream.  torch.cuda.current_stream() costs ~14 us, a forward makes ~150 launches:
+    the engine refreshes the cached handle once per forward / backward call."""
+    if refresh:
+        _STREAM[0] = torch.cuda.current_stream().cuda_stream
+    return _STREAM[0]
+
+
+def _named_params(module: nn.Module):
+    """(names, parameters) of the module, cached: the module tree is fixed after construction, and walking 69 (D) or
+    771 (G) parameters through named_parameters() on every call is milliseconds of host time per training step."""
+    c = module.__dict__.get("_esrp_named_params")
+    if c is None or len(c[1]) == 0 or c[1][0] is not next(iter(module.parameters())):
+        names, params = [], []
+        for k, v in module.named_parameters():
+            names.append(k)
+            params.append(v)
+        c = (names, params)
+        module.__dict__["_esrp_named_params"] = c
+    return c
 
 
 def _rearrange_k4s2(w4: torch.Tensor) -> torch.Tensor:
@@ -182,6 +203,7 @@ class DiscriminatorEngine:
     def forward(self, module: nn.Module, x: torch.Tensor, saved: Optional[list] = None) -> torch.Tensor:
         if x.dim() != 4 or x.dtype != torch.float32 or x.device != self.device:
             raise RuntimeError("Discriminator_VGG_128 forward expects an fp32 NCHW CUDA tensor")
+        _stream(refresh=True)
         n = x.shape[0]
         if x.shape[2] != 128 or x.shape[3] != 128:
             raise RuntimeError("Discriminator_VGG_128 expects 128x128 inputs (classifier is Linear(512*4*4, 100))")
@@ -341,11 +363,11 @@ class DiscriminatorEngine:
 
     def backward(self, module: nn.Module, saved: list, dout: torch.Tensor, need_dx: bool, need_params: bool):
         """Returns (dx NCHW fp32 or None, {parameter name: gradient view} or {}, flat gradient buffer or None)."""
-        st = _stream()
+        st = _stream(refresh=True)
         head = saved[-1]
         n, flat, h0 = head["n"], head["flat"], head["h0"]
-        names = [k for k, _ in module.named_parameters()]
-        params = dict(module.named_parameters())
+        names, plist = _named_params(module)
+        params = dict(zip(names, plist))
         grads: Dict[str, torch.Tensor] = {}
         flatg = None
         if need_params:
@@ -432,17 +454,18 @@ class _DiscriminatorFn(torch.autograd.Function):
         if flat is not None:
             from .autograd import allreduce_flat
             allreduce_flat(ctx.module, flat)
-        names = [k for k, _ in ctx.module.named_parameters()]
+        names = _named_params(ctx.module)[0]
         return (None, None, dx) + tuple(grads[k] if (need_params and nd) else None for k, nd in zip(names, needs))
 
 
 def discriminator_apply(module: nn.Module, x: torch.Tensor) -> torch.Tensor:
-    needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters()))
+    plist = _named_params(module)[1]
+    needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in plist))
     engines = module.__dict__.setdefault("_engines", {})
     eng = engines.get(x.device)
     if eng is None:
         eng = DiscriminatorEngine(module, x.device)
         engines[x.device] = eng
     if needs_grad:
-        return _DiscriminatorFn.apply(module, eng, x.contiguous(), *[p for _, p in module.named_parameters()])
+        return _DiscriminatorFn.apply(module, eng, x.contiguous(), *plist)
     return eng.forward(module, x.contiguous())
