@@ -215,23 +215,38 @@ def main_ours(args):
     def barrier():
         if dist is not None:
             dist.barrier()
-        torch.cuda.synchronize()
+        torch.cuda.synchronize()   # all streams of the device, the copy stream included
 
     def step_resident():
         return net(x_dev)
 
+    # e2e: every step copies its input from pinned host memory, runs the public module call and copies the fp32 result
+    # back; the device->host copy of step i runs on a copy stream and overlaps the forward of step i+1 (two pinned
+    # result buffers), as a serving loop would do it.  All copies of all steps lie inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    y_hosts = [y_host, torch.empty_like(y_host).pin_memory()]
+    e2e_i = [0]
+
     def step_e2e():
         xd = x_host.to(dev, non_blocking=True)
         y = net(xd)
-        y_host.copy_(y, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ready)
+            y_hosts[e2e_i[0] & 1].copy_(y, non_blocking=True)
+            y.record_stream(copy_stream)
+        e2e_i[0] += 1
         return y
 
-    def timed(fn, steps):
+    def timed(fn, steps, join=None):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
         for _ in range(steps):
             fn()
+        if join is not None:
+            torch.cuda.current_stream().wait_stream(join)   # the last device->host copy ends inside the timed region
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -251,7 +266,7 @@ def main_ours(args):
         clocks = sampler.stop() if sampler else None
         for _ in range(2):
             step_e2e()
-        ms_e2e = timed(step_e2e, args.steps)
+        ms_e2e = timed(step_e2e, args.steps, join=copy_stream)
     train = train_strong = None
     if not args.no_train:
         try:

@@ -229,3 +229,104 @@ def test_generator_backward_operator_graph_without_sign_sensitivity(cuda_dev, nf
         noises.append(row)
     emu_y, emu_g = _oracle_grads(x, sd, nb, dy, True, noises, emulate=True)
     _compare(net, emu_g, f"one-sided activations ({sign:+.0f})", REL_L2_LINEAR, 0.9998)
+
+
+def test_graph_replay_draws_new_noise_and_matches_oracle(cuda_dev):
+    """From the second forward/backward pair of a shape on, the engine replays CUDA graphs of its launch plans; the
+    Philox key of the noise launches is read from device memory, so a replay must (i) draw NEW noise per call,
+    (ii) reproduce under the same torch seed, (iii) still match the oracle fed with that call's draws."""
+    lib = _lib.load()
+    nf, nb, n, h, w = 32, 1, 2, 16, 16
+    sd = O.synth_state_dict_g(3, 3, nf, nb, seed=23)
+    net = _make(sd, nf, nb, cuda_dev).train()
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(n, 3, h, w, generator=g)
+    dy = torch.randn(n, 3, 4 * h, 4 * w, generator=g)
+    torch.manual_seed(7)
+    outs = []
+    for it in range(3):
+        net.zero_grad()
+        y = net(x.to(cuda_dev))
+        (y * dy.to(cuda_dev)).sum().backward()
+        outs.append(y.detach().cpu())
+    assert not torch.equal(outs[0], outs[1]) and not torch.equal(outs[1], outs[2])
+    seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + net._step) & 0xFFFFFFFFFFFFFFFF
+    noises = []
+    for i in range(nb):
+        row = []
+        for r in range(3):
+            buf = np.empty(n * h * w * nf, dtype=np.float32)
+            assert lib.esrp_philox_normal_host(seed, (i * 3 + r) << 36, buf.size, buf.ctypes.data) == 0
+            row.append(torch.from_numpy(buf).reshape(n, h, w, nf).permute(0, 3, 1, 2).contiguous())
+        noises.append(row)
+    _check(net, x, sd, nb, dy, "third (replayed) call", training=True, noises=noises, y=outs[2])
+    # same torch seed + same call count => same draws
+    net2 = _make(sd, nf, nb, cuda_dev).train()
+    torch.manual_seed(7)
+    with torch.no_grad():
+        pass
+    y2 = None
+    for it in range(3):
+        net2.zero_grad()
+        y2 = net2(x.to(cuda_dev))
+        (y2 * dy.to(cuda_dev)).sum().backward()
+    assert torch.equal(y2.detach().cpu(), outs[2])
+
+
+@pytest.mark.parametrize("upscale", [1, 2])
+def test_generator_backward_other_upscales(cuda_dev, upscale):
+    """architecture.py:51-69: upscale 2 has one upconv block, upscale 1 none (the HR convs then run at LR resolution and
+    the shortcut gradient comes straight from HR_conv0's data gradient)."""
+    import torch.nn.functional as F
+    nf, nb, n, h, w = 32, 1, 2, 12, 20
+    n_up = {1: 0, 2: 1}[upscale]
+    full = O.synth_state_dict_g(3, 3, nf, nb, seed=33)
+    # reference key layout for n_up upconv blocks (sequential() flattening): model.{3,6} upconvs, then HR_conv0 / HR_conv1
+    remap = {"model.0": "model.0", "model.1": "model.1"}
+    src_hr0, src_hr1 = "model.8", "model.10"
+    sd = {}
+    for k, v in full.items():
+        head = ".".join(k.split(".")[:2])
+        if head in ("model.0", "model.1"):
+            sd[k] = v
+    for u in range(n_up):
+        for suf in ("weight", "bias"):
+            sd[f"model.{3 + 3 * u}.{suf}"] = full[f"model.{3 + 3 * u}.{suf}"]
+    for suf in ("weight", "bias"):
+        sd[f"model.{2 + 3 * n_up}.{suf}"] = full[f"{src_hr0}.{suf}"]
+        sd[f"model.{4 + 3 * n_up}.{suf}"] = full[f"{src_hr1}.{suf}"]
+    net = E.RRDBNet(3, 3, nf, nb, upscale=upscale)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(cuda_dev).eval()
+    g = torch.Generator().manual_seed(upscale)
+    x = torch.rand(n, 3, h, w, generator=g)
+    dy = torch.randn(n, 3, upscale * h, upscale * w, generator=g)
+    y = net(x.to(cuda_dev))
+    (y * dy.to(cuda_dev)).sum().backward()
+
+    def ref_forward(xx, sdd):
+        cv = lambda t, key: F.conv2d(t, _r(sdd[key + ".weight"]), sdd[key + ".bias"], padding=1)
+        fea = cv(_r(xx), "model.0")
+        t = fea
+        p = "model.1.sub.0."
+        rr = t
+        for r in (1, 2, 3):
+            q = f"{p}RDB{r}."
+            xb = _r(t)
+            x1 = _r(F.leaky_relu(cv(xb, q + "conv1.0"), 0.2))
+            x2 = _r(F.leaky_relu(cv(torch.cat((xb, x1), 1), q + "conv2.0"), 0.2) + F.conv2d(xb, _r(sdd[q + "conv1x1.weight"])))
+            x3 = _r(F.leaky_relu(cv(torch.cat((xb, x1, x2), 1), q + "conv3.0"), 0.2))
+            x4 = _r(F.leaky_relu(cv(torch.cat((xb, x1, x2, x3), 1), q + "conv4.0"), 0.2) + x2)
+            t = 0.2 * cv(torch.cat((xb, x1, x2, x3, x4), 1), q + "conv5.0") + t
+        t = 0.2 * t + rr
+        t = _r(cv(_r(t), "model.1.sub.1") + fea)
+        for u in range(n_up):
+            t = _r(F.leaky_relu(cv(F.interpolate(t, scale_factor=2, mode="nearest"), f"model.{3 + 3 * u}"), 0.2))
+        t = _r(F.leaky_relu(cv(t, f"model.{2 + 3 * n_up}"), 0.2))
+        return cv(t, f"model.{4 + 3 * n_up}")
+
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ry = ref_forward(x, sdg)
+    (ry * dy).sum().backward()
+    assert (y.detach().cpu() - ry.detach()).abs().max().item() <= 3e-2 * ry.detach().std().item()
+    _compare(net, {k: v.grad for k, v in sdg.items()}, f"upscale {upscale} vs bf16-storage oracle", REL_L2, COS)
