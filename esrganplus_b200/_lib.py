@@ -76,7 +76,7 @@ class Conv3x3Desc(C.Structure):
     ]
 
 
-WGRAD_MAX_UNITS = 16
+WGRAD_MAX_UNITS = 256
 
 
 class DgradGroup(C.Structure):

@@ -82,7 +82,7 @@ constexpr int kWgXPitch = 80;             // bytes per pixel row of the X tile (
 constexpr int kWgYPitch = 144;            // bytes per pixel row of the dY tile (64 ch bf16 + 16 pad)
 
 struct WgradParams {
-  esrp_wgrad_unit_t u[ESRP_WGRAD_MAX_UNITS];
+  esrp_wgrad_unit_t u[kMmaMaxUnits];
   int num_units, splits;
   int n, h, w;
   int tw, tw_log2, tr;       // tile = tr rows x tw columns, tr * tw == kWgTilePx
@@ -479,6 +479,7 @@ int plan_wgrad(const esrp_wgrad_unit_t* units, int num_units, int n, int h, int 
       if (strict) return 1;
     }
   }
+  if (num_units > kMmaMaxUnits) return set_error("wgrad: the mma.sync kernel takes at most %d units per launch (got %d)", kMmaMaxUnits, num_units);
   out->tc = 0;
   out->num_bias = 0;
   WgradParams& p = *reinterpret_cast<WgradParams*>(out->params);

@@ -8,15 +8,19 @@
 namespace esrp {
 
 // tcgen05 weight-gradient kernel (esrp_wgrad_tc.cu): a job = one 64-channel chunk of X against one 128-channel slab of dY
-constexpr int kTcMaxJobs = 8;
+constexpr int kTcMaxJobs = 64;
+constexpr int kTcMaxMaps = 4;   // distinct X / dY tensors per launch (jobs share tensor maps)
+constexpr int kMmaMaxUnits = 16;  // units per launch of the mma.sync kernel
 struct WgTcJobInfo {
   int xc0, dyc0;       // first channel of the X chunk / of the dY slab
-  int y_panels, pad_;  // 64-channel panels of the slab that exist in the tensor (1 or 2)
+  short y_panels;      // 64-channel panels of the slab that exist in the tensor (1 or 2)
+  short mx, my;        // tensor-map indices
+  short pad_;
   float* acc[2][2];    // [32-channel group of the chunk][64-column block of the slab] unit accumulators, or nullptr
 };
 struct alignas(64) WgTcParams {
-  CUtensorMap tmx[kTcMaxJobs];
-  CUtensorMap tmy[kTcMaxJobs];
+  CUtensorMap tmx[kTcMaxMaps];
+  CUtensorMap tmy[kTcMaxMaps];
   WgTcJobInfo job[kTcMaxJobs];
   int num_jobs, splits;
   int n, h, w;
@@ -26,7 +30,7 @@ struct alignas(64) WgTcParams {
 };
 
 struct WgradLaunch {
-  alignas(64) unsigned char params[sizeof(WgTcParams)];
+  alignas(64) unsigned char params[sizeof(WgTcParams) > 1024 ? sizeof(WgTcParams) : 1024];
   int grid = 0;
   int smem = 0;
   int tc = 0;                // 1: tcgen05 kernel (params holds WgTcParams), 0: mma.sync kernel (WgradParams)

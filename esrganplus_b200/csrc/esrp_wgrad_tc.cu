@@ -121,8 +121,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) wgrad_tc_kernel(const __grid_co
     for (int s = 0; s < kTcMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2); }
     mbar_init(&done_bar, 2);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    tma_prefetch_desc(&p.tmx[job]);
-    tma_prefetch_desc(&p.tmy[job]);
+    tma_prefetch_desc(&p.tmx[J.mx]);
+    tma_prefetch_desc(&p.tmy[J.my]);
   }
   if (warp == 1) {
     tmem_alloc(&tmem_holder, 512);
@@ -148,9 +148,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) wgrad_tc_kernel(const __grid_co
         // the tap group needs two of the three kernel rows: rows y0-1 .. y0+tr-1 (taps 0-4) or y0 .. y0+tr (taps 5-8);
         // a slab whose upper 64 channels lie beyond the tensor skips that panel (its accumulator rows are never read)
         mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(p.x_bytes + J.y_panels * kTcYPanel));
-        tma_load_4d(xs, &p.tmx[job], &full_bar[s], J.xc0, x0 - 1, y0 - 1 + tg, img);
-        tma_load_4d(ys, &p.tmy[job], &full_bar[s], J.dyc0, x0, y0, img);
-        if (J.y_panels > 1) tma_load_4d(ys + kTcYPanel, &p.tmy[job], &full_bar[s], J.dyc0 + 64, x0, y0, img);
+        tma_load_4d(xs, &p.tmx[J.mx], &full_bar[s], J.xc0, x0 - 1, y0 - 1 + tg, img);
+        tma_load_4d(ys, &p.tmy[J.my], &full_bar[s], J.dyc0, x0, y0, img);
+        if (J.y_panels > 1) tma_load_4d(ys + kTcYPanel, &p.tmy[J.my], &full_bar[s], J.dyc0 + 64, x0, y0, img);
       }
     }
   } else if (warp == 1 || warp == 6) {
@@ -255,8 +255,17 @@ int plan_wgrad_tc(const esrp_wgrad_unit_t* units, int num_units, int n, int h, i
   memset(&p, 0, sizeof(p));
   out->num_bias = 0;
   struct Key { const void* x; int xct, xc0; const void* dy; int dct, dyc0; };
+  struct Ten { const void* p; int ct; };
   Key keys[kTcMaxJobs];
-  int nj = 0;
+  Ten xt[kTcMaxMaps], yt[kTcMaxMaps];
+  int nj = 0, nxt = 0, nyt = 0;
+  auto ten_index = [](Ten* tab, int* cnt, const void* ptr, int ct) -> int {
+    for (int i = 0; i < *cnt; ++i)
+      if (tab[i].p == ptr && tab[i].ct == ct) return i;
+    if (*cnt == kTcMaxMaps) return -1;
+    tab[*cnt] = Ten{ptr, ct};
+    return (*cnt)++;
+  };
   for (int i = 0; i < num_units; ++i) {
     const esrp_wgrad_unit_t& u = units[i];
     if ((u.x_c0 % 32) || (u.dy_c0 % 64)) return set_error("wgrad(tc): unit %d channel offsets must be multiples of 32 / 64", i);
@@ -267,11 +276,15 @@ int plan_wgrad_tc(const esrp_wgrad_unit_t* units, int num_units, int n, int h, i
     for (; j < nj; ++j)
       if (keys[j].x == k.x && keys[j].xc0 == k.xc0 && keys[j].dy == k.dy && keys[j].dyc0 == k.dyc0) break;
     if (j == nj) {
-      if (nj == kTcMaxJobs) return set_error("wgrad(tc): more than %d jobs in one launch", kTcMaxJobs);
+      if (nj == kTcMaxJobs) return set_error("wgrad(tc): more than %d (chunk, slab) jobs in one launch", kTcMaxJobs);
+      const int mx = ten_index(xt, &nxt, k.x, k.xct), my = ten_index(yt, &nyt, k.dy, k.dct);
+      if (mx < 0 || my < 0) return set_error("wgrad(tc): more than %d distinct tensors in one launch", kTcMaxMaps);
       keys[nj] = k;
       p.job[nj].xc0 = k.xc0;
       p.job[nj].dyc0 = k.dyc0;
       p.job[nj].y_panels = (k.dyc0 + 64 < k.dct) ? 2 : 1;
+      p.job[nj].mx = static_cast<short>(mx);
+      p.job[nj].my = static_cast<short>(my);
       ++nj;
     }
     const int g = (u.x_c0 % 64) / 32, b = (u.dy_c0 - k.dyc0) / 64;
@@ -307,10 +320,10 @@ int plan_wgrad_tc(const esrp_wgrad_unit_t* units, int num_units, int n, int h, i
   if (splits < 1) splits = 1;
   if (splits > p.tiles_total) splits = p.tiles_total;
   p.splits = splits;
-  for (int j = 0; j < nj; ++j) {
-    if (make_nhwc_tmap(&p.tmx[j], keys[j].x, n, h, w, keys[j].xct, 64, p.xw, p.tr + 1)) return 1;
-    if (make_nhwc_tmap(&p.tmy[j], keys[j].dy, n, h, w, keys[j].dct, 64, p.tw, p.tr)) return 1;
-  }
+  for (int i = 0; i < nxt; ++i)
+    if (make_nhwc_tmap(&p.tmx[i], xt[i].p, n, h, w, xt[i].ct, 64, p.xw, p.tr + 1)) return 1;
+  for (int i = 0; i < nyt; ++i)
+    if (make_nhwc_tmap(&p.tmy[i], yt[i].p, n, h, w, yt[i].ct, 64, p.tw, p.tr)) return 1;
   out->grid = nj * 2 * splits;
   out->smem = p.stages * p.stage_bytes + 1024;
   out->tc = 1;

@@ -317,8 +317,11 @@ class DiscriminatorEngine:
         scat["acc"][nu:] = np.uint64(bias_base) + np.arange(nblk, dtype=np.uint64) * np.uint64(256)
         scat["dst"][nu:] = db.data_ptr()
         st = _stream()
-        for u0 in range(0, nu, _lib.WGRAD_MAX_UNITS):
-            cnt = min(_lib.WGRAD_MAX_UNITS, nu - u0)
+        # one call covers whole 64-channel input chunks (2 groups x nblk units each); a launch holds <= 64 (chunk, slab) jobs
+        slabs = (nblk + 1) // 2
+        per_call = max(1, min(_lib.WGRAD_MAX_UNITS // (2 * nblk), 64 // slabs)) * 2 * nblk
+        for u0 in range(0, nu, per_call):
+            cnt = min(per_call, nu - u0)
             part = np.ascontiguousarray(units[u0:u0 + cnt])
             _lib.check(self.lib.esrp_conv3x3_wgrad(part.ctypes.data_as(C.POINTER(_lib.WgradUnit)), cnt, n, gh, gw, 0, st),
                        "esrp_conv3x3_wgrad")

@@ -225,7 +225,7 @@ typedef struct esrp_dgrad_group {
 int esrp_pack_dgrad_weights(const esrp_dgrad_group_t* groups_host, int32_t num_groups, int32_t layout,
                             int32_t row0, int32_t rows, int32_t kc, int32_t bn, void* out, void* stream);
 
-#define ESRP_WGRAD_MAX_UNITS 16
+#define ESRP_WGRAD_MAX_UNITS 256 /* per call; the units of one call may span at most 4 tensors and 64 (chunk, slab) jobs */
 /* acc[tap = ky*3+kx][c < 64][i < 32] += sum_px dy[px][dy_c0 + c] * x[px + (ky-1, kx-1)][x_c0 + i]
  * (zero padding; dy channels beyond dy_ctotal read as zero); bias_acc[c] += sum_px dy[px][dy_c0 + c]. */
 typedef struct esrp_wgrad_unit {
