@@ -33,31 +33,33 @@ __global__ void s2d_pad_kernel(const uint4* __restrict__ src, uint4* __restrict_
 
 // Per-channel sum and sum of squares over the valid [h, w] region of x [n, hp, wp, c] fp32.
 // One block per (channel group of 32, pixel slab); partial sums via atomics on double accumulators.
-__global__ void bn_stats_kernel(const float* __restrict__ x, int n, int h, int w, int hp, int wp, int c,
-                                double* __restrict__ sums) {
-  const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int lane_px = threadIdx.x >> 5;            // 8 pixel lanes per block (256 threads)
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, int n, int h, int w, int hp, int wp, int c,
+                                                       double* __restrict__ sums) {
+  // thread = 4 channels (one 16-byte load) x one of 32 pixel lanes; block = 32 channels
+  const int c4 = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int ch = blockIdx.x * 32 + c4 * 4;
   const long long npx = static_cast<long long>(n) * h * w;
-  double s = 0.0, ss = 0.0;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
   if (ch < c) {
-    for (long long pi = static_cast<long long>(blockIdx.y) * 8 + lane_px; pi < npx; pi += static_cast<long long>(gridDim.y) * 8) {
+    for (long long pi = static_cast<long long>(blockIdx.y) * 32 + pl; pi < npx; pi += static_cast<long long>(gridDim.y) * 32) {
       const int xw = static_cast<int>(pi % w);
       const long long t = pi / w;
       const int yh = static_cast<int>(t % h);
       const int img = static_cast<int>(t / h);
-      const float v = x[((static_cast<size_t>(img) * hp + yh) * wp + xw) * c + ch];
-      s += v;
-      ss += static_cast<double>(v) * v;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + ((static_cast<size_t>(img) * hp + yh) * wp + xw) * c + ch));
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+      ss[0] = fmaf(v.x, v.x, ss[0]); ss[1] = fmaf(v.y, v.y, ss[1]); ss[2] = fmaf(v.z, v.z, ss[2]); ss[3] = fmaf(v.w, v.w, ss[3]);
     }
   }
-  __shared__ double sh[2][8][32];
-  sh[0][lane_px][threadIdx.x & 31] = s;
-  sh[1][lane_px][threadIdx.x & 31] = ss;
+  __shared__ float sh[2][32][33];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { sh[0][pl][c4 * 4 + j] = s[j]; sh[1][pl][c4 * 4 + j] = ss[j]; }
   __syncthreads();
-  if (lane_px == 0 && ch < c) {
-    for (int i = 1; i < 8; ++i) { s += sh[0][i][threadIdx.x & 31]; ss += sh[1][i][threadIdx.x & 31]; }
-    atomicAdd(&sums[ch], s);
-    atomicAdd(&sums[c + ch], ss);
+  if (threadIdx.x < 64) {
+    const int which = threadIdx.x >> 5, cc = threadIdx.x & 31;
+    double t = 0.0;
+    for (int i = 0; i < 32; ++i) t += sh[which][i][cc];
+    if (blockIdx.x * 32 + cc < c) atomicAdd(&sums[which * c + blockIdx.x * 32 + cc], t);
   }
 }
 
@@ -125,8 +127,9 @@ int esrp_bn_stats_nhwc_f32(const float* x, int32_t n, int32_t h, int32_t w, int3
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   ESRP_CUDA_OK(cudaMemsetAsync(sums2c, 0, sizeof(double) * 2 * c, s));
   const long long npx = static_cast<long long>(n) * h * w;
-  int slabs = static_cast<int>((npx + 8 * 64 - 1) / (8 * 64));
-  if (slabs > 296) slabs = 296;
+  // latency-bound streaming reduction: many slabs (32 pixels per block iteration), capped at 4 blocks per SM and group
+  int slabs = static_cast<int>((npx + 127) / 128);
+  if (slabs > 592) slabs = 592;
   if (slabs < 1) slabs = 1;
   dim3 grid((c + 31) / 32, slabs);
   bn_stats_kernel<<<grid, 256, 0, s>>>(x, n, h, w, hp, wp, c, sums2c);
@@ -174,36 +177,52 @@ __device__ __forceinline__ float bn_dzb(float z, float d, float scale, float shi
 
 // sums[ch] += sum dzb, sums[c+ch] += sum dzb * xhat over the valid [h, w] region.
 // dout: bf16 NHWC [n,h,w,c] (dout_nchw == NULL) or fp32 NCHW-flat [n, c*h*w].
-__global__ void bn_bwd_reduce_kernel(const float* __restrict__ z, const __nv_bfloat16* __restrict__ dout,
-                                     const float* __restrict__ dout_nchw, int n, int h, int w, int hp, int wp, int c,
-                                     const float* __restrict__ coef, double* __restrict__ sums) {
-  const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int lane_px = threadIdx.x >> 5;
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ z, const __nv_bfloat16* __restrict__ dout,
+                                                            const float* __restrict__ dout_nchw, int n, int h, int w, int hp, int wp,
+                                                            int c, const float* __restrict__ coef, double* __restrict__ sums) {
+  const int c4 = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int ch = blockIdx.x * 32 + c4 * 4;
   const long long npx = static_cast<long long>(n) * h * w;
-  double s1 = 0.0, s2 = 0.0;
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
   if (ch < c) {
-    const float mean = coef[ch], rstd = coef[c + ch], scale = coef[2 * c + ch], shift = coef[3 * c + ch];
-    for (long long pi = static_cast<long long>(blockIdx.y) * 8 + lane_px; pi < npx; pi += static_cast<long long>(gridDim.y) * 8) {
+    float mean[4], rstd[4], scale[4], shift[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      mean[j] = coef[ch + j]; rstd[j] = coef[c + ch + j]; scale[j] = coef[2 * c + ch + j]; shift[j] = coef[3 * c + ch + j];
+    }
+    for (long long pi = static_cast<long long>(blockIdx.y) * 32 + pl; pi < npx; pi += static_cast<long long>(gridDim.y) * 32) {
       const int xw = static_cast<int>(pi % w);
       const long long t = pi / w;
       const int yh = static_cast<int>(t % h);
       const int img = static_cast<int>(t / h);
-      const float zv = z[((static_cast<size_t>(img) * hp + yh) * wp + xw) * c + ch];
-      const float d = dout_nchw ? dout_nchw[((static_cast<size_t>(img) * c + ch) * h + yh) * w + xw]
-                                : __bfloat162float(dout[static_cast<size_t>(pi) * c + ch]);
-      const float dzb = bn_dzb(zv, d, scale, shift);
-      s1 += dzb;
-      s2 += static_cast<double>(dzb) * ((zv - mean) * rstd);
+      const float4 zq = __ldg(reinterpret_cast<const float4*>(z + ((static_cast<size_t>(img) * hp + yh) * wp + xw) * c + ch));
+      const float zv[4] = {zq.x, zq.y, zq.z, zq.w};
+      float d[4];
+      if (dout_nchw) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d[j] = dout_nchw[((static_cast<size_t>(img) * c + ch + j) * h + yh) * w + xw];
+      } else {
+        const uint2 q = __ldg(reinterpret_cast<const uint2*>(dout + static_cast<size_t>(pi) * c + ch));
+        d[0] = __uint_as_float(q.x << 16); d[1] = __uint_as_float(q.x & 0xFFFF0000u);
+        d[2] = __uint_as_float(q.y << 16); d[3] = __uint_as_float(q.y & 0xFFFF0000u);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float dzb = bn_dzb(zv[j], d[j], scale[j], shift[j]);
+        s1[j] += dzb;
+        s2[j] = fmaf(dzb, (zv[j] - mean[j]) * rstd[j], s2[j]);
+      }
     }
   }
-  __shared__ double sh[2][8][32];
-  sh[0][lane_px][threadIdx.x & 31] = s1;
-  sh[1][lane_px][threadIdx.x & 31] = s2;
+  __shared__ float sh[2][32][33];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { sh[0][pl][c4 * 4 + j] = s1[j]; sh[1][pl][c4 * 4 + j] = s2[j]; }
   __syncthreads();
-  if (lane_px == 0 && ch < c) {
-    for (int i = 1; i < 8; ++i) { s1 += sh[0][i][threadIdx.x & 31]; s2 += sh[1][i][threadIdx.x & 31]; }
-    atomicAdd(&sums[ch], s1);
-    atomicAdd(&sums[c + ch], s2);
+  if (threadIdx.x < 64) {
+    const int which = threadIdx.x >> 5, cc = threadIdx.x & 31;
+    double t = 0.0;
+    for (int i = 0; i < 32; ++i) t += sh[which][i][cc];
+    if (blockIdx.x * 32 + cc < c) atomicAdd(&sums[which * c + blockIdx.x * 32 + cc], t);
   }
 }
 
@@ -306,8 +325,9 @@ int esrp_bn_bwd_reduce(const float* z, const void* dout_bf16, const float* dout_
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   ESRP_CUDA_OK(cudaMemsetAsync(sums2c, 0, sizeof(double) * 2 * c, s));
   const long long npx = static_cast<long long>(n) * h * w;
-  int slabs = static_cast<int>((npx + 8 * 64 - 1) / (8 * 64));
-  if (slabs > 296) slabs = 296;
+  // latency-bound streaming reduction: many slabs (32 pixels per block iteration), capped at 4 blocks per SM and group
+  int slabs = static_cast<int>((npx + 127) / 128);
+  if (slabs > 592) slabs = 592;
   if (slabs < 1) slabs = 1;
   dim3 grid((c + 31) / 32, slabs);
   esrp::bn_bwd_reduce_kernel<<<grid, 256, 0, s>>>(z, static_cast<const __nv_bfloat16*>(dout_bf16), dout_nchw_f32, n, h, w, hp,
