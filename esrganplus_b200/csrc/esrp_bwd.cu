@@ -242,39 +242,47 @@ __global__ void __launch_bounds__(kWgThreads, 2) conv3x3_wgrad_kernel(const __gr
 // ------------------------------------------------------------------------------------------------
 // kind 0: conv weight: dst[(co0 + c) * w_i + ci0 + i][tap] = scale * acc[tap][col0 + c][i]   c < ncols, i < nci
 // kind 1: flat copy:   dst[i] = scale * acc[i]                                              i < ncols
-__global__ void wgrad_scatter_kernel(const esrp_scatter_entry_t* __restrict__ tab, int num, float* const* __restrict__ dst_ptrs) {
-  for (int e = blockIdx.x; e < num; e += gridDim.x) {
-    const esrp_scatter_entry_t s = tab[e];
-    float* dst = dst_ptrs ? dst_ptrs[s.dst_index] : s.dst;
-    if (dst == nullptr) continue;
-    if (s.kind == 1) {
-      for (int i = threadIdx.x; i < s.ncols; i += blockDim.x) dst[s.dst_off + i] = s.scale * s.acc[i];
-      continue;
+__global__ void __launch_bounds__(256) wgrad_scatter_kernel(const esrp_scatter_entry_t* __restrict__ tab, int num,
+                                                            float* const* __restrict__ dst_ptrs) {
+  // block = (entry, group of 8 accumulator columns): the [9][8][32] slice is staged through shared memory so that both
+  // the reads (32 consecutive input channels) and the writes (runs of nci * 9 or nci * 16 floats per output channel)
+  // are coalesced
+  __shared__ float tile[9][8][33];
+  const int e = blockIdx.x >> 3, cg = blockIdx.x & 7;
+  if (e >= num) return;
+  const esrp_scatter_entry_t s = tab[e];
+  float* dst = dst_ptrs ? dst_ptrs[s.dst_index] : s.dst;
+  if (dst == nullptr) return;
+  if (s.kind == 1) {
+    for (int i = cg * 256 + threadIdx.x; i < s.ncols; i += 8 * 256) dst[s.dst_off + i] = s.scale * s.acc[i];
+    return;
+  }
+  const int c0 = cg * 8;
+  if (c0 >= s.ncols) return;
+  const int nc = min(8, s.ncols - c0);
+  for (int i = threadIdx.x; i < 9 * 8 * 32; i += 256) {
+    const int ci = i & 31, c = (i >> 5) & 7, tap = i >> 8;
+    tile[tap][c][ci] = (c < nc && ci < s.nci) ? s.acc[(static_cast<size_t>(tap) * 64 + s.col0 + c0 + c) * 32 + ci] : 0.f;
+  }
+  __syncthreads();
+  if (s.kind == 2) {
+    // 4x4 / stride-2 conv evaluated as a 3x3 conv over the space-to-depth tensor (esrp_s2d_pad_nhwc_bf16):
+    // unit channel ci0 + i = (a*2+b) * w_i + ci, tap (A+1, B+1) -> dW4[co][ci][2A+a][2B+b]; taps with A or B < 0 are zero
+    const int ab = s.ci0 / s.w_i, cib = s.ci0 - ab * s.w_i;
+    const int a = ab >> 1, b = ab & 1;
+    for (int i = threadIdx.x; i < nc * s.nci * 4; i += 256) {
+      const int q = i & 3, ci = (i >> 2) % s.nci, c = (i >> 2) / s.nci;
+      const int A = q >> 1, B = q & 1;
+      dst[s.dst_off + (static_cast<size_t>(s.co0 + c0 + c) * s.w_i + cib + ci) * 16 + (2 * A + a) * 4 + (2 * B + b)] =
+          s.scale * tile[(A + 1) * 3 + (B + 1)][c][ci];
     }
-    const int total = s.ncols * s.nci * 9;
-    if (s.kind == 2) {
-      // 4x4 / stride-2 conv evaluated as a 3x3 conv over the space-to-depth tensor (esrp_s2d_pad_nhwc_bf16):
-      // unit channel ci0 + i = (a*2+b) * w_i + ci, tap (A+1, B+1) -> dW4[co][ci][2A+a][2B+b]; taps with A or B < 0 are zero
-      const int ab = s.ci0 / s.w_i, cib = s.ci0 - ab * s.w_i;
-      const int a = ab >> 1, b = ab & 1;
-      for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int tap = i % 9;
-        const int ci = (i / 9) % s.nci;
-        const int c = i / (9 * s.nci);
-        const int A = tap / 3 - 1, B = tap % 3 - 1;
-        if (A < 0 || B < 0) continue;
-        const float v = s.acc[(static_cast<size_t>(tap) * 64 + s.col0 + c) * 32 + ci];
-        dst[s.dst_off + (static_cast<size_t>(s.co0 + c) * s.w_i + cib + ci) * 16 + (2 * A + a) * 4 + (2 * B + b)] = s.scale * v;
-      }
-      continue;
-    }
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-      const int tap = i % 9;
-      const int ci = (i / 9) % s.nci;
-      const int c = i / (9 * s.nci);
-      const float v = s.acc[(static_cast<size_t>(tap) * 64 + s.col0 + c) * 32 + ci];
-      dst[s.dst_off + (static_cast<size_t>(s.co0 + c) * s.w_i + s.ci0 + ci) * 9 + tap] = s.scale * v;
-    }
+    return;
+  }
+  const int run = s.nci * 9;
+  for (int i = threadIdx.x; i < nc * run; i += 256) {
+    const int c = i / run, r = i - c * run;
+    const int ci = r / 9, tap = r - ci * 9;
+    dst[s.dst_off + (static_cast<size_t>(s.co0 + c0 + c) * s.w_i + s.ci0) * 9 + r] = s.scale * tile[tap][c][ci];
   }
 }
 
@@ -550,8 +558,7 @@ int run_conv1x1_bwd(int nf, const void* x, int x_ctotal, const void* dx2, int d_
 
 int run_scatter(const esrp_scatter_entry_t* tab_dev, int num, float* const* dst_ptrs_dev, cudaStream_t stream) {
   if (num < 1) return 0;
-  int grid = num < 4096 ? num : 4096;
-  wgrad_scatter_kernel<<<grid, 256, 0, stream>>>(tab_dev, num, dst_ptrs_dev);
+  wgrad_scatter_kernel<<<num * 8, 256, 0, stream>>>(tab_dev, num, dst_ptrs_dev);
   ESRP_CUDA_OK(cudaGetLastError());
   return 0;
 }
