@@ -267,6 +267,32 @@ def main_ours(args):
         for _ in range(2):
             step_e2e()
         ms_e2e = timed(step_e2e, args.steps, join=copy_stream)
+    # the same loop fed and drained as 8-bit images (RRDBNet.forward_uint8: the /255, BGR<->RGB, clamp, x255, round of
+    # test_image/test.py:31-40 on the device): 4x smaller copies in both directions
+    e2e_u8 = None
+    try:
+        xu_host = (x_host.permute(0, 2, 3, 1) * 255).round().to(torch.uint8).contiguous().pin_memory()
+        yu_hosts = [torch.empty(BATCH, 4 * TILE, 4 * TILE, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
+
+        def step_u8():
+            y = net.forward_uint8(xu_host.to(dev, non_blocking=True))
+            ready = torch.cuda.Event()
+            ready.record()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ready)
+                yu_hosts[e2e_i[0] & 1].copy_(y, non_blocking=True)
+                y.record_stream(copy_stream)
+            e2e_i[0] += 1
+
+        with torch.no_grad():
+            for _ in range(2):
+                step_u8()
+            ms_u8 = timed(step_u8, args.steps, join=copy_stream)
+        e2e_u8 = {"value": BATCH * OUT_MP_PER_TILE * world / (ms_u8 / args.steps * 1e-3), "unit": "MP/s",
+                  "h2d_bytes_per_step": xu_host.numel() * world, "d2h_bytes_per_step": yu_hosts[0].numel() * world,
+                  "ms_per_step": ms_u8 / args.steps, "api": "RRDBNet.forward_uint8 (uint8 HWC in/out, plumbing on the device)"}
+    except Exception as e:
+        e2e_u8 = {"error": f"{type(e).__name__}: {e}"[:300]}
     train = train_strong = None
     if not args.no_train:
         try:
@@ -320,6 +346,7 @@ def main_ours(args):
                          "flops_per_step_per_gpu": flops_step},
             "cpu_baseline": cpu,
             "clocks": clocks,
+            "e2e_uint8": e2e_u8,
             "train": train,
             "train_strong": train_strong,
         }

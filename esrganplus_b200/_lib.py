@@ -155,6 +155,13 @@ SYMBOLS = {
     "esrp_rrdbnet_num_launches": (C.c_int32, [C.c_void_p]),
     "esrp_rrdbnet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_void_p]),
+    "esrp_u8hwc_to_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_int32, C.c_void_p]),
+    "esrp_nchw_f32_to_u8hwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_void_p]),
+    "esrp_rrdbnet_workspace_bytes_u8": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    "esrp_rrdbnet_forward_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "esrp_rrdbnet_train_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     "esrp_rrdbnet_train_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                              C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_void_p]),

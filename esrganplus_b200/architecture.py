@@ -79,6 +79,19 @@ class _GeneratorBase(nn.Module):
         object.__setattr__(self, "_step", self._step + 1)
         return (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._step) & 0xFFFFFFFFFFFFFFFF
 
+    def forward_uint8(self, img: torch.Tensor, bgr: bool = True) -> torch.Tensor:
+        """Not part of the reference surface: 8-bit images in, 8-bit images out, with the host
+        plumbing of test_image/test.py:31-40 (``/255``, BGR<->RGB, ``clamp_(0,1)``, ``(x*255).round()``) done on the
+        device — a 4x smaller device->host copy and no numpy pass.  img: uint8 [n,h,w,in_nc] CUDA tensor (cv2 order when
+        `bgr`); always the eval-mode network, no gradient."""
+        if not img.is_cuda:
+            raise RuntimeError("esrganplus_b200.RRDBNet runs on CUDA (sm_100a) only")
+        from .discriminator import _named_params
+        names, plist = _named_params(self)
+        eng = self._engine_for(img.device)
+        eng.sync_weights(dict(zip(names, plist)))
+        return eng.forward_u8(img, bgr)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if not x.is_cuda:
             raise RuntimeError("esrganplus_b200.RRDBNet runs on CUDA (sm_100a) only; there is no CPU path "

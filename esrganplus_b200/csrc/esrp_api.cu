@@ -233,6 +233,34 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float
   }
 }
 
+// Image plumbing of test_image/test.py on the device.
+// :31-35  cv2 image (uint8, HWC, BGR) -> /255 -> RGB -> float CHW : here straight to the NHWC bf16 network input
+__global__ void u8hwc_to_nhwc_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long npx, int c,
+                                     int c_pad, int swap) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < npx * c_pad;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % c_pad);
+    const long long px = i / c_pad;
+    float v = 0.f;
+    if (ch < c) v = static_cast<float>(src[px * c + ((swap && c == 3) ? 2 - ch : ch)]) / 255.0f;
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+// :37-39  output.clamp_(0, 1) -> RGB->BGR, CHW->HWC -> (output * 255.0).round() : NCHW fp32 -> uint8 HWC
+__global__ void nchw_to_u8hwc_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int c, long long hw, int swap) {
+  const long long img = blockIdx.y;
+  const float* s = src + img * c * hw;
+  uint8_t* d = dst + img * c * hw;
+  for (long long px = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; px < hw;
+       px += static_cast<long long>(gridDim.x) * blockDim.x) {
+    for (int ch = 0; ch < c; ++ch) {
+      float v = s[static_cast<long long>((swap && c == 3) ? 2 - ch : ch) * hw + px];
+      v = fminf(fmaxf(v, 0.f), 1.f);            // clamp_ (NaN -> 0 like fmaxf; the reference would propagate it)
+      d[px * c + ch] = static_cast<uint8_t>(rintf(v * 255.0f));   // numpy round: half to even
+    }
+  }
+}
+
 // nearest x2 upsample, NHWC bf16, 16-byte vectors: each thread copies one 8-channel vector to 4 outputs.
 __global__ void upsample2x_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int n, int h,
                                   int w, int cv) {
@@ -359,6 +387,29 @@ int esrp_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int32_t n, int32_t c
   dim3 grid((hw + 31) / 32, n);
   nhwc_to_nchw_kernel<<<grid, 256, c * 33 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(src), dst, c, hw, c_total);
+  ESRP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int esrp_u8hwc_to_nhwc_bf16(const uint8_t* src, void* dst, int32_t n, int32_t h, int32_t w, int32_t c, int32_t c_pad,
+                            int32_t bgr, void* stream) {
+  if (!src || !dst || c < 1 || c_pad < c) return set_error("u8hwc_to_nhwc: bad arguments");
+  const long long npx = static_cast<long long>(n) * h * w;
+  long long blocks = (npx * c_pad + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  u8hwc_to_nhwc_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), npx, c, c_pad, bgr);
+  ESRP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int esrp_nchw_f32_to_u8hwc(const float* src, uint8_t* dst, int32_t n, int32_t c, int32_t h, int32_t w, int32_t bgr,
+                           void* stream) {
+  if (!src || !dst || c < 1 || n < 1) return set_error("nchw_to_u8hwc: bad arguments");
+  const long long hw = static_cast<long long>(h) * w;
+  long long bx = (hw + 255) / 256;
+  if (bx > 1024) bx = 1024;
+  nchw_to_u8hwc_kernel<<<dim3(static_cast<unsigned>(bx), n), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, c, hw, bgr);
   ESRP_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -432,7 +432,7 @@ int32_t esrp_rrdbnet_num_launches(const esrp_rrdbnet_t* h) {
 int esrp_rrdbnet_forward(esrp_rrdbnet_t* h, const float* x, float* y, int32_t n, int32_t hh, int32_t w,
                          void* workspace, int64_t workspace_bytes, int32_t training, uint64_t seed, void* stream) {
   Rrdbnet* m = reinterpret_cast<Rrdbnet*>(h);
-  if (!m || !x || !y || !workspace) return set_error("rrdbnet_forward: null argument");
+  if (!m || (!x && !m->x_u8) || !y || !workspace) return set_error("rrdbnet_forward: null argument");
   if (!m->weights_loaded) return set_error("rrdbnet_forward: weights not loaded");
   if (n < 1 || hh < 1 || w < 1) return set_error("rrdbnet_forward: bad shape");
   const int64_t need = esrp_rrdbnet_workspace_bytes(h, n, hh, w);
@@ -470,7 +470,11 @@ int esrp_rrdbnet_forward(esrp_rrdbnet_t* h, const float* x, float* y, int32_t n,
     ++step_idx;
     switch (st.kind) {
       case Step::kPackInput:
-        if (esrp_nchw_f32_to_nhwc_bf16(x, st.dst, st.n, st.c, st.h, st.w, st.c_pad, stream)) return 1;
+        if (m->x_u8) {
+          if (esrp_u8hwc_to_nhwc_bf16(m->x_u8, st.dst, st.n, st.h, st.w, st.c, st.c_pad, m->x_bgr, stream)) return 1;
+        } else if (esrp_nchw_f32_to_nhwc_bf16(x, st.dst, st.n, st.c, st.h, st.w, st.c_pad, stream)) {
+          return 1;
+        }
         break;
       case Step::kUpsample:
         if (esrp_upsample2x_nhwc_bf16(st.src, st.dst, st.n, st.h, st.w, st.c, stream)) return 1;
@@ -486,6 +490,30 @@ int esrp_rrdbnet_forward(esrp_rrdbnet_t* h, const float* x, float* y, int32_t n,
     }
   }
   return 0;
+}
+
+int64_t esrp_rrdbnet_workspace_bytes_u8(const esrp_rrdbnet_t* h, int32_t n, int32_t hh, int32_t w) {
+  const Rrdbnet* m = reinterpret_cast<const Rrdbnet*>(h);
+  const int64_t base = esrp_rrdbnet_workspace_bytes(h, n, hh, w);
+  if (base < 0) return -1;
+  return base + static_cast<int64_t>(n) * m->out_nc * hh * m->upscale * w * m->upscale * 4;
+}
+
+int esrp_rrdbnet_forward_u8(esrp_rrdbnet_t* h, const uint8_t* x, uint8_t* y, int32_t n, int32_t hh, int32_t w, void* workspace,
+                            int64_t workspace_bytes, int32_t bgr, void* stream) {
+  Rrdbnet* m = reinterpret_cast<Rrdbnet*>(h);
+  if (!m || !x || !y || !workspace) return set_error("rrdbnet_forward_u8: null argument");
+  const int64_t base = esrp_rrdbnet_workspace_bytes(h, n, hh, w);
+  const int64_t need = esrp_rrdbnet_workspace_bytes_u8(h, n, hh, w);
+  if (base < 0 || workspace_bytes < need)
+    return set_error("rrdbnet_forward_u8: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
+  float* y32 = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + base);
+  m->x_u8 = x;
+  m->x_bgr = bgr;
+  const int rc = esrp_rrdbnet_forward(h, nullptr, y32, n, hh, w, workspace, base, 0, 0, stream);
+  m->x_u8 = nullptr;
+  if (rc) return rc;
+  return esrp_nchw_f32_to_u8hwc(y32, y, n, m->out_nc, hh * m->upscale, w * m->upscale, bgr, stream);
 }
 
 }  // extern "C"

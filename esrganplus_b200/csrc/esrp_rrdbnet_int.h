@@ -60,6 +60,8 @@ struct Rrdbnet {
   bool g_zeroed = false;
   std::vector<Step> steps;
   TrainState* train = nullptr;        // training plan + dgrad weight cache (lazily created)
+  const uint8_t* x_u8 = nullptr;     // set for the duration of esrp_rrdbnet_forward_u8: the input is an 8-bit HWC image
+  int x_bgr = 0;
   PackJob* pack_jobs_dev = nullptr;   // job table of the batched forward-weight repack (one entry per ConvW)
   std::vector<PackJob> pack_jobs_host;
 };

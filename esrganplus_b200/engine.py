@@ -97,6 +97,33 @@ class GeneratorEngine:
                        "esrp_rrdbnet_forward")
         return y
 
+    def forward_u8(self, img: torch.Tensor, bgr: bool = True) -> torch.Tensor:
+        """uint8 HWC images [n,h,w,in_nc] (cv2 order when bgr) -> uint8 HWC [n,s*h,s*w,out_nc]: the /255, channel swap,
+        clamp, x255, round of test_image/test.py:31-40 run on the device (esrp_rrdbnet_forward_u8)."""
+        if img.dim() != 4 or img.dtype != torch.uint8 or img.device != self.device or img.shape[3] != self.cfg[0]:
+            raise RuntimeError(f"forward_u8 expects a uint8 [n,h,w,{self.cfg[0]}] tensor on {self.device}")
+        img = img.contiguous()
+        n, h, w, _ = img.shape
+        key = ("u8", n, h, w)
+        ws = self._ws.get(key)
+        if ws is None:
+            nbytes = self.lib.esrp_rrdbnet_workspace_bytes_u8(self.handle, n, h, w)
+            if nbytes < 0:
+                raise RuntimeError("esrp_rrdbnet_workspace_bytes_u8 failed")
+            if len(self._ws) >= 4:
+                self._ws.clear()
+            ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        base = ws.data_ptr()
+        aligned = (base + 1023) // 1024 * 1024
+        y = torch.empty((n, h * self.upscale, w * self.upscale, self.out_nc), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.esrp_rrdbnet_forward_u8(self.handle, img.data_ptr(), y.data_ptr(), n, h, w, aligned,
+                                                        ws.numel() - (aligned - base), int(bool(bgr)),
+                                                        torch.cuda.current_stream(self.device).cuda_stream),
+                       "esrp_rrdbnet_forward_u8")
+        return y
+
     @property
     def num_launches(self) -> int:
         return self.lib.esrp_rrdbnet_num_launches(self.handle)

@@ -153,6 +153,13 @@ int esrp_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int32_t n, int32_t c
                                int32_t w, int32_t c_pad, void* stream);
 int esrp_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int32_t n, int32_t c, int32_t h,
                                int32_t w, int32_t c_total, void* stream);
+/* Image plumbing of the caller, on the device.
+ * test_image/test.py:31-35: uint8 HWC image (cv2: BGR, bgr != 0 swaps to RGB) -> /255 -> NHWC bf16 network input;
+ * test_image/test.py:37-39: NCHW fp32 output -> clamp(0,1) -> x255 -> round half to even -> uint8 HWC (RGB -> BGR if bgr). */
+int esrp_u8hwc_to_nhwc_bf16(const uint8_t* src, void* dst, int32_t n, int32_t h, int32_t w, int32_t c, int32_t c_pad,
+                            int32_t bgr, void* stream);
+int esrp_nchw_f32_to_u8hwc(const float* src, uint8_t* dst, int32_t n, int32_t c, int32_t h, int32_t w, int32_t bgr,
+                           void* stream);
 /* nn.Upsample(scale_factor=2, mode='nearest') on NHWC bf16 (block.py:319). */
 int esrp_upsample2x_nhwc_bf16(const void* src, void* dst, int32_t n, int32_t h, int32_t w,
                               int32_t c, void* stream);
@@ -294,6 +301,13 @@ int32_t esrp_rrdbnet_num_launches(const esrp_rrdbnet_t* h);
 int esrp_rrdbnet_forward(esrp_rrdbnet_t* h, const float* x, float* y, int32_t n, int32_t hgt, int32_t w,
                          void* workspace, int64_t workspace_bytes, int32_t training, uint64_t seed,
                          void* stream);
+
+/* The same forward fed and drained as 8-bit images (what test_image/test.py:31-40 does around model(img_LR) on the host):
+ * x: uint8 [n,h,w,in_nc] HWC, y: uint8 [n,upscale*h,upscale*w,out_nc] HWC, both BGR when bgr != 0 (cv2 order).  The
+ * workspace must hold esrp_rrdbnet_workspace_bytes_u8() bytes (the fp32 result lives at its end). */
+int64_t esrp_rrdbnet_workspace_bytes_u8(const esrp_rrdbnet_t* h, int32_t n, int32_t hgt, int32_t w);
+int esrp_rrdbnet_forward_u8(esrp_rrdbnet_t* h, const uint8_t* x, uint8_t* y, int32_t n, int32_t hgt, int32_t w,
+                            void* workspace, int64_t workspace_bytes, int32_t bgr, void* stream);
 
 /* ---- training (the autograd graph of architecture.py:76-78 as driven by SRRaGAN_model.py:120,140) ----
  * esrp_rrdbnet_train_forward computes the same y as esrp_rrdbnet_forward and keeps, in `workspace`, what the

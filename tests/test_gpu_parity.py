@@ -217,6 +217,36 @@ def test_rrdbnet_config1_matches_reference_fixture(cuda_dev, golden_dir, cls):
     assert diff.max() <= 2 and (diff > 0).mean() < 0.25, (diff.max(), (diff > 0).mean())
 
 
+def test_uint8_plumbing_on_device_matches_host_plumbing(cuda_dev, golden_dir):
+    """RRDBNet.forward_uint8 (esrp_rrdbnet_forward_u8): the /255, BGR<->RGB, clamp, x255, round of
+    test_image/test.py:31-40 on the device.  (i) bit-identical to the same plumbing done on the host around the fp32
+    module call; (ii) within the 8-bit tolerance of the reference fixture; (iii) a batch of ragged-size images."""
+    g = _golden(golden_dir, "rrdbnet_c1_nb1_nf32.npz")
+    sd = O.synth_state_dict_g(3, 3, 32, 1, seed=21)
+    net = _make(E.RRDBNet, sd, 32, 1, cuda_dev)
+
+    def host_plumbing(img_u8):
+        img = img_u8 * 1.0 / 255
+        t = torch.from_numpy(np.transpose(img[:, :, [2, 1, 0]], (2, 0, 1))).float().unsqueeze(0).to(cuda_dev)
+        out = net(t).data.squeeze().float().cpu().clamp_(0, 1).numpy()
+        return (np.transpose(out[[2, 1, 0], :, :], (1, 2, 0)) * 255.0).round().astype("uint8")
+
+    dev_out = net.forward_uint8(torch.from_numpy(g["img_u8"]).unsqueeze(0).to(cuda_dev)).cpu().numpy()[0]
+    assert dev_out.shape == (128, 128, 3) and dev_out.dtype == np.uint8
+    assert np.array_equal(dev_out, host_plumbing(g["img_u8"]))
+    diff = np.abs(dev_out.astype(int) - g["out_u8"].astype(int))
+    assert diff.max() <= 2 and (diff > 0).mean() < 0.25, (diff.max(), (diff > 0).mean())
+    rng = np.random.default_rng(5)
+    imgs = rng.integers(0, 256, size=(3, 19, 37, 3), dtype=np.uint8)
+    outs = net.forward_uint8(torch.from_numpy(imgs).to(cuda_dev)).cpu().numpy()
+    assert outs.shape == (3, 76, 148, 3)
+    for i in range(3):
+        assert np.array_equal(outs[i], host_plumbing(imgs[i])), i
+    # RGB-ordered input/output (bgr=False) is the channel-reversed problem
+    rgb = net.forward_uint8(torch.from_numpy(imgs[:, :, :, ::-1].copy()).to(cuda_dev), bgr=False).cpu().numpy()
+    assert np.array_equal(rgb[:, :, :, ::-1], outs)
+
+
 def test_rrdbnet_nb23_matches_reference_fixture(cuda_dev, golden_dir):
     g = _golden(golden_dir, "rrdbnet_nb23_nf64.npz")
     sd = O.synth_state_dict_g(3, 3, 64, 23, seed=31)
