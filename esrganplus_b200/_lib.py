@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ESRP_MAX_CHUNKS = 8
+ESRP_MAX_CHUNKS = 32
 LAYOUT_TILE = 0   # kx-stacked RM x CW tiles (conv3x3_tc.cuh): any width, narrow images
 LAYOUT_ROW = 1    # ky-stacked row streaming (conv3x3_row.cuh): images wider than ~64 px, bn <= 32
 

@@ -9,6 +9,8 @@
 
 namespace esrp {
 
+constexpr int kPackMaxChunks = 8;  // the generator's convs have <= 5 chunks / 6 data-gradient groups; keeps the job table small
+
 struct PackJob {
   int type;  // 0: forward operator (esrp_pack_conv3x3_weights, transpose = 0), 1: data-gradient operator (esrp_pack_dgrad_weights)
   int layout, row0, rows, kc, bn, num_chunks;
@@ -16,14 +18,14 @@ struct PackJob {
   // type 0
   const float* w;
   int w_o, w_i;
-  int lc0[ESRP_MAX_CHUNKS];
+  int lc0[kPackMaxChunks];
   const float* aux;
   int aux_cin, aux_chunks;
   const float* bias_src;  // [w_o] or NULL
   float* bias_dst;        // [bn], zero padded, or NULL
   // type 1
   int num_groups;
-  esrp_dgrad_group_t g[2 * ESRP_MAX_CHUNKS];
+  esrp_dgrad_group_t g[2 * kPackMaxChunks];
 };
 
 int run_pack_batch(const PackJob* jobs_dev, int num_jobs, cudaStream_t stream);

@@ -38,7 +38,7 @@ assert _UNIT_DT.itemsize == C.sizeof(_lib.WgradUnit) and _SCAT_DT.itemsize == C.
 ACC_BLOCK = 9 * 64 * 32
 
 SLICE = 32            # output channels per launch
-MAX_CHUNKS = {_lib.LAYOUT_ROW: 3, _lib.LAYOUT_TILE: 8}   # K chunks per launch (weights must fit in smem)
+MAX_CHUNKS = {_lib.LAYOUT_ROW: 3, _lib.LAYOUT_TILE: _lib.ESRP_MAX_CHUNKS}   # K chunks per launch (the row kernel keeps its weights resident in shared memory, the tile kernel streams them)
 
 
 _STREAM = [0]

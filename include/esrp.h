@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ESRP_MAX_CHUNKS 8
+#define ESRP_MAX_CHUNKS 32
 
 /* Tiling overrides for esrp_conv3x3_t.variant (0 = library default): bits 0-3 force the number
  * of M-tile accumulator slots per CTA tile (1..5), bits 4-7 force log2 of the M-tile width in
