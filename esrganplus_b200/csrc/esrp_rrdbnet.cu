@@ -95,6 +95,8 @@ int ensure_layouts(Rrdbnet* m, int w, cudaStream_t s) {
     return 0;
   };
   if (want(m->fea, w) || want(m->rdb, w) || want(m->trunk, w)) return 1;
+  for (auto& c : m->rdb5w)
+    if (c.layout != ESRP_LAYOUT_TILE && pack_one(m, &c, ESRP_LAYOUT_TILE, s)) return 1;
   int ww = w;
   for (int u = 0; u < m->n_up; ++u) {
     ww *= 2;
@@ -132,6 +134,12 @@ int esrp_rrdbnet_create(int32_t in_nc, int32_t out_nc, int32_t nf, int32_t nb, i
       for (int k = 0; k < 5; ++k)
         define_conv(m, &m->rdb, p + "conv" + std::to_string(k + 1) + ".0", nf + k * gc, k == 4 ? nf : gc, nf, k * gc,
                     k == 1 ? aux_key : -1);
+      if (nf == 64) {
+        ConvW wide = m->rdb[m->rdb.size() - 2];  // first conv5 slice: same tensors, all 64 output channels
+        wide.row0 = 0; wide.rows = 64; wide.bn = 64;
+        wide.layout = ESRP_LAYOUT_TILE;
+        m->rdb5w.push_back(wide);
+      }
     }
   }
   define_conv(m, &m->trunk, "model.1.sub." + std::to_string(nb), nf, nf, nf, 0);
@@ -343,8 +351,10 @@ int build_plan(Rrdbnet* m, int n, int h, int w, uint8_t* wsp, int training, cuda
       uint8_t* out_b = wsp + ws.tb[slot];
       uint8_t* out_f = wsp + ws.tf[slot];
       uint8_t* G = wsp + ws.g;
-      for (int k = 0; k < m->per_rdb; ++k) {
-        const ConvW& c = m->rdb[(static_cast<size_t>(i) * 3 + r) * m->per_rdb + k];
+      const bool wide5 = !m->rdb5w.empty() && layout_for_width(w) == ESRP_LAYOUT_TILE;
+      for (int k = 0; k < (wide5 ? 5 : m->per_rdb); ++k) {
+        const ConvW& c = (wide5 && k == 4) ? m->rdb5w[static_cast<size_t>(i) * 3 + r]
+                                           : m->rdb[(static_cast<size_t>(i) * 3 + r) * m->per_rdb + k];
         base_desc(m, c, n, h, w, &d);
         d.src[0] = cur_b; d.src_ctotal[0] = nf;
         d.src[1] = G; d.src_ctotal[1] = 4 * gc;

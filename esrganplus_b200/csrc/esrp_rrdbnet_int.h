@@ -48,6 +48,8 @@ struct Rrdbnet {
   // every logical conv is a list of <= 32-output-channel launches
   std::vector<ConvW> fea, trunk, up[2], hr0, hr1;
   std::vector<ConvW> rdb;  // nb*3*per_rdb: conv1..4, then conv5 as nf/32 output-channel slices
+  std::vector<ConvW> rdb5w;  // nf == 64: conv5 as ONE 64-wide slice, tile layout only (the tile kernel streams its weights,
+                             // so narrow images / training crops run conv5 in one launch instead of two)
   int per_rdb = 5;
   uint8_t* wbuf = nullptr;
   size_t wbytes = 0;
@@ -81,6 +83,7 @@ template <class F>
 int for_each_conv(Rrdbnet* m, F&& f) {
   for (auto& c : m->fea) if (f(&c)) return 1;
   for (auto& c : m->rdb) if (f(&c)) return 1;
+  for (auto& c : m->rdb5w) if (f(&c)) return 1;
   for (auto& c : m->trunk) if (f(&c)) return 1;
   for (int u = 0; u < m->n_up; ++u)
     for (auto& c : m->up[u]) if (f(&c)) return 1;
