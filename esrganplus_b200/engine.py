@@ -206,16 +206,33 @@ class GeneratorEngine:
                                                       torch.cuda.current_stream(self.device).cuda_stream),
                        "esrp_rrdbnet_backward")
         self._train_token += 1  # consumed
+        # one split call instead of 771 slice ops; slices are padded to 16 bytes, only odd-sized tensors need a narrow
+        sizes, numels = self._grad_split_sizes()
+        parts = flat.split(sizes)
         grads = []
-        for shp, off, need in zip(shapes, offs.tolist(), needs):
+        for part, shp, numel, need in zip(parts, shapes, numels, needs):
             if not need:
                 grads.append(None)
-                continue
-            numel = 1
-            for d in shp:
-                numel *= d
-            grads.append(flat[off:off + numel].view(shp))
+            elif part.numel() == numel:
+                grads.append(part.view(shp))
+            else:
+                grads.append(part[:numel].view(shp))
         return grads, flat
+
+    def _grad_split_sizes(self):
+        c = getattr(self, "_gsplit", None)
+        if c is None:
+            shapes, offs, total = self._grad_layout()
+            o = offs.tolist() + [total]
+            sizes = [int(o[i + 1] - o[i]) for i in range(len(shapes))]
+            numels = []
+            for shp in shapes:
+                n = 1
+                for d in shp:
+                    n *= d
+                numels.append(n)
+            c = self._gsplit = (sizes, numels)
+        return c
 
     def train_launches(self):
         return (self.lib.esrp_rrdbnet_train_num_launches(self.handle, 0),
