@@ -424,10 +424,11 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
             ext_pre_and_mask<GC>(p, pix, ch0, v);
           }
           if (p.noise) {
+            const unsigned long long nseed = p.seed_ptr ? __ldg(p.seed_ptr) : p.seed;  // graph replays read the key from memory
 #pragma unroll 1
             for (int i = 0; i < GC; i += 4) {
               float z[4];
-              philox_normal4(p.seed_ptr ? __ldg(p.seed_ptr) : p.seed,
+              philox_normal4(nseed,
                              p.offset + (pix * static_cast<unsigned long long>(p.noise_ctotal) + p.noise_c0 + ch0 + i) / 4, z);
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj) {

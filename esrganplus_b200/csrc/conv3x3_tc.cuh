@@ -421,12 +421,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
             ext_pre_and_mask<GC>(p, pix, ch0, v);
           }
           if (p.noise) {
+            const unsigned long long nseed = p.seed_ptr ? __ldg(p.seed_ptr) : p.seed;  // graph replays read the key from memory
             // y = t + N(0,1) * sigma * t  (block.py:117-121); one Philox counter per 4 channels of
             // element index e = pixel * noise_ctotal + noise_c0 + channel.
 #pragma unroll
             for (int i = 0; i < GC; i += 4) {
               float z[4];
-              philox_normal4(p.seed_ptr ? __ldg(p.seed_ptr) : p.seed,
+              philox_normal4(nseed,
                              p.offset + (pix * static_cast<unsigned long long>(p.noise_ctotal) + p.noise_c0 + ch0 + i) / 4, z);
 #pragma unroll
               for (int j = 0; j < 4; ++j) v[i + j] = fmaf(z[j] * p.sigma, v[i + j], v[i + j]);
