@@ -131,14 +131,13 @@ def train_leg(torch, dev, world, rank, dist, steps=8, warmup=3, global_batch=32,
     import esrganplus_b200 as E
     from esrganplus_b200.autograd import broadcast_parameters, data_parallel
     from esrganplus_b200.gan_step import GanTrainStep
-    from oracle import esrgan_oracle as O  # synthetic weights only
+    from esrganplus_b200.synth import random_state_dict_d, random_state_dict_g
     bs = max(1, global_batch // world)
     netG = E.RRDBNet(3, 3, NF, NB)
-    sd = O.synth_state_dict_g(3, 3, NF, NB, seed=31)
     # ~ kaiming x 0.1 with zero bias, what networks.py:103-104 does for G before training
-    netG.load_state_dict({k: v * (0.1 if k.endswith("weight") else 0.0) for k, v in sd.items()}, strict=True)
+    netG.load_state_dict(random_state_dict_g(3, 3, NF, NB, seed=31, scale=0.1, zero_bias=True), strict=True)
     netD = E.Discriminator_VGG_128(3, 64)
-    netD.load_state_dict(O.synth_state_dict_d(3, 64, seed=32), strict=True)
+    netD.load_state_dict(random_state_dict_d(3, 64, seed=32), strict=True)
     netG, netD = netG.to(dev).train(), netD.to(dev).train()
     if dist is not None:
         broadcast_parameters(netG)
@@ -186,7 +185,7 @@ def train_leg(torch, dev, world, rank, dist, steps=8, warmup=3, global_batch=32,
 def main_ours(args):
     import torch
     import esrganplus_b200 as E
-    from oracle import esrgan_oracle as O  # synthetic weights + cpu_baseline leg only
+    from esrganplus_b200.synth import random_state_dict_g
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -201,7 +200,7 @@ def main_ours(args):
         dist = dist_
         dist.init_process_group("nccl", device_id=dev)
 
-    sd = O.synth_state_dict_g(3, 3, NF, NB, seed=31)       # random-init weights of the named architecture
+    sd = random_state_dict_g(3, 3, NF, NB, seed=31)        # random-init weights of the named architecture
     net = E.RRDBNet(3, 3, NF, NB, gc=32, upscale=4)
     net.load_state_dict(sd, strict=True)
     net = net.to(dev).eval()

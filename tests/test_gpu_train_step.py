@@ -7,7 +7,7 @@ Tolerances: losses within 2 % (+1e-4 absolute), D logit means within 2e-2, per-t
 fp32 reference, the discriminator here has random synthetic weights and BatchNorm over a batch of 2, and its input
 gradient is then chaotic in the forward precision — the fp32 oracle and the same oracle at bf16 storage precision
 differ from EACH OTHER by rel-L2 0.4 / cos 0.91 on this very input, while the kernels match the bf16-storage oracle
-to 0.11 / 0.993 (tools/diag_gphase.py; the per-network tests hold the tight bounds).  What this test pins is the
+to 0.11 / 0.993 (tests/diag/diag_gphase.py; the per-network tests hold the tight bounds).  What this test pins is the
 solver logic: phases, freezing, the relativistic losses, both Adam steps, BatchNorm statistics.
 """
 import os

@@ -28,7 +28,7 @@ def main():
     import esrganplus_b200 as E
     from esrganplus_b200.autograd import data_parallel
     from esrganplus_b200.gan_step import GanTrainStep
-    from oracle import esrgan_oracle as O  # synthetic weights only
+    from esrganplus_b200.synth import random_state_dict_d, random_state_dict_g
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -41,10 +41,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     bs = args.batch if args.weak else max(1, args.batch // world)
     netG = E.RRDBNet(3, 3, 64, args.nb)
-    sd = O.synth_state_dict_g(3, 3, 64, args.nb, seed=31)
-    netG.load_state_dict({k: v * (0.1 if k.endswith("weight") else 0.0) for k, v in sd.items()})  # ~ kaiming x 0.1 (networks.py:104)
+    netG.load_state_dict(random_state_dict_g(3, 3, 64, args.nb, seed=31, scale=0.1, zero_bias=True))  # ~ kaiming x 0.1 (networks.py:104)
     netD = E.Discriminator_VGG_128(3, 64)
-    netD.load_state_dict(O.synth_state_dict_d(3, 64, seed=32))
+    netD.load_state_dict(random_state_dict_d(3, 64, seed=32))
     netG, netD = netG.to(dev).train(), netD.to(dev).train()
     if world > 1:
         data_parallel(netG)

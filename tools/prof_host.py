@@ -3,11 +3,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import esrganplus_b200 as E
 from esrganplus_b200.gan_step import GanTrainStep
-from oracle import esrgan_oracle as O
+from esrganplus_b200.synth import random_state_dict_d, random_state_dict_g
 dev = torch.device("cuda:0")
-netG = E.RRDBNet(3, 3, 64, 23); sd = O.synth_state_dict_g(3, 3, 64, 23, seed=31)
-netG.load_state_dict({k: v * (0.1 if k.endswith("weight") else 0.0) for k, v in sd.items()})
-netD = E.Discriminator_VGG_128(3, 64); netD.load_state_dict(O.synth_state_dict_d(3, 64, seed=32))
+netG = E.RRDBNet(3, 3, 64, 23)
+netG.load_state_dict(random_state_dict_g(3, 3, 64, 23, seed=31, scale=0.1, zero_bias=True))
+netD = E.Discriminator_VGG_128(3, 64); netD.load_state_dict(random_state_dict_d(3, 64, seed=32))
 netG, netD = netG.to(dev).train(), netD.to(dev).train()
 step = GanTrainStep(netG, netD)
 lr = torch.rand(32, 3, 32, 32, device=dev); hr = torch.rand(32, 3, 128, 128, device=dev)

@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 import esrganplus_b200 as E
-from oracle import esrgan_oracle as O  # synthetic weights only
+from esrganplus_b200.synth import random_state_dict_d, random_state_dict_g
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=16)
@@ -25,7 +25,7 @@ ap.add_argument("--bwd", action="store_true", help="profile one training forward
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 net = E.RRDBNet(3, 3, 64, a.nb)
-net.load_state_dict(O.synth_state_dict_g(3, 3, 64, a.nb, seed=31))
+net.load_state_dict(random_state_dict_g(3, 3, 64, a.nb, seed=31))
 net = net.to(dev)
 net.train(a.train)
 for p in net.parameters():
