@@ -121,6 +121,9 @@ SYMBOLS = {
                                          C.c_void_p, C.c_void_p]),
     "esrp_bn_apply_nhwc": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "esrp_streams_create": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p)]),
+    "esrp_streams_fork": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32]),
+    "esrp_streams_join": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32]),
     "esrp_linear_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int32, C.c_void_p]),
     "esrp_bn_bwd_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

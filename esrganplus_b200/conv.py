@@ -24,7 +24,7 @@ def _i32_array(vals: Sequence[int]):
 def pack_conv3x3_weights(w_oihw: torch.Tensor, kc: int, bn: int, chunk_lc0: Sequence[int],
                          w_aux: Optional[torch.Tensor] = None, aux_chunks: int = 0, row0: int = 0,
                          rows: Optional[int] = None, transpose: bool = False,
-                         layout: int = _lib.LAYOUT_TILE) -> torch.Tensor:
+                         layout: int = _lib.LAYOUT_TILE, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[O, I, 3, 3] fp32 (device) -> pre-swizzled bf16 UMMA B tiles [chunk][ky][kx*bn + r (, conv1x1)][kc]
     (opaque bytes).  `w_aux` is the bias-free 1x1 conv [O, I_aux(,1,1)] fused on the first `aux_chunks`
     chunks; `transpose` packs the data-gradient operator (see include/esrp.h)."""
@@ -41,7 +41,9 @@ def pack_conv3x3_weights(w_oihw: torch.Tensor, kc: int, bn: int, chunk_lc0: Sequ
         w_aux = w_aux.reshape(w_aux.shape[0], w_aux.shape[1]).contiguous()
         aux_ptr, aux_cin = w_aux.data_ptr(), w_aux.shape[1]
     nbytes = lib.esrp_packed_conv3x3_bytes(len(chunk_lc0), kc, bn, int(aux_chunks > 0))
-    out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    if out is None:
+        out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    assert out.numel() == nbytes and out.dtype == torch.uint8   # `out=`: repack in place (cached descriptors keep their pointer)
     _lib.check(lib.esrp_pack_conv3x3_weights(w.data_ptr(), w_o, w_i, int(transpose), layout, row0, rows, kc, bn,
                                              len(chunk_lc0), _i32_array(chunk_lc0), aux_ptr, aux_cin, aux_chunks,
                                              out.data_ptr(), _stream_ptr()),
@@ -196,7 +198,7 @@ def upsample2x_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
 # backward-pass helpers (esrp_pack_dgrad_weights / esrp_conv3x3_wgrad / ... in include/esrp.h)
 # ------------------------------------------------------------------------------------------------
 def pack_dgrad_weights(groups: Sequence[Optional[tuple]], row0: int, rows: int, kc: int, bn: int,
-                       layout: int = _lib.LAYOUT_TILE) -> torch.Tensor:
+                       layout: int = _lib.LAYOUT_TILE, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """groups: per 32-channel K group either None (zero weights) or (w_oihw fp32 cuda, co0, scale)."""
     lib = _lib.load()
     arr = (_lib.DgradGroup * len(groups))()
@@ -212,7 +214,8 @@ def pack_dgrad_weights(groups: Sequence[Optional[tuple]], row0: int, rows: int, 
         dev = w.device
         arr[i].w, arr[i].w_o, arr[i].w_i, arr[i].co0, arr[i].scale = w.data_ptr(), w.shape[0], w.shape[1], co0, scale
     chunks = (len(groups) * 32 + kc - 1) // kc
-    out = torch.empty(lib.esrp_packed_conv3x3_bytes(chunks, kc, bn, 0), dtype=torch.uint8, device=dev)
+    if out is None:
+        out = torch.empty(lib.esrp_packed_conv3x3_bytes(chunks, kc, bn, 0), dtype=torch.uint8, device=dev)
     _lib.check(lib.esrp_pack_dgrad_weights(arr, len(groups), layout, row0, rows, kc, bn, out.data_ptr(), _stream_ptr()),
                "esrp_pack_dgrad_weights")
     return out

@@ -452,3 +452,54 @@ int esrp_bn_bwd_finalize(const double* sums2c, double count, int32_t batch_stats
 }
 
 }  // extern "C"
+
+// -------------------------------------------------------------------------------------------------
+// Fork / join over a small pool of side streams: the output-channel slices of a deep discriminator layer are
+// independent launches that each fill only 7-70 of the 148 SMs; issued on different streams they run concurrently.
+// -------------------------------------------------------------------------------------------------
+namespace esrp {
+static cudaEvent_t next_event() {
+  static thread_local cudaEvent_t ring[64];
+  static thread_local int pos = 0, made = 0;
+  if (made < 64) {
+    if (cudaEventCreateWithFlags(&ring[made], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    return ring[made++];
+  }
+  // a recorded event may be re-recorded as soon as the waits on it have been ENQUEUED (they captured its state)
+  cudaEvent_t e = ring[pos];
+  pos = (pos + 1) & 63;
+  return e;
+}
+}  // namespace esrp
+
+extern "C" {
+
+int esrp_streams_create(int32_t n, void** out_streams) {
+  if (!out_streams || n < 1 || n > 16) return esrp::set_error("streams_create: n must be in 1..16");
+  for (int i = 0; i < n; ++i) {
+    cudaStream_t s;
+    ESRP_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    out_streams[i] = s;
+  }
+  return 0;
+}
+
+int esrp_streams_fork(void* main_stream, void* const* sides, int32_t n) {
+  cudaEvent_t e = esrp::next_event();
+  if (!e) return esrp::set_error("streams_fork: cudaEventCreate failed");
+  ESRP_CUDA_OK(cudaEventRecord(e, static_cast<cudaStream_t>(main_stream)));
+  for (int i = 0; i < n; ++i) ESRP_CUDA_OK(cudaStreamWaitEvent(static_cast<cudaStream_t>(sides[i]), e, 0));
+  return 0;
+}
+
+int esrp_streams_join(void* main_stream, void* const* sides, int32_t n) {
+  for (int i = 0; i < n; ++i) {
+    cudaEvent_t e = esrp::next_event();
+    if (!e) return esrp::set_error("streams_join: cudaEventCreate failed");
+    ESRP_CUDA_OK(cudaEventRecord(e, static_cast<cudaStream_t>(sides[i])));
+    ESRP_CUDA_OK(cudaStreamWaitEvent(static_cast<cudaStream_t>(main_stream), e, 0));
+  }
+  return 0;
+}
+
+}  // extern "C"

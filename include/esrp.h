@@ -207,6 +207,12 @@ int esrp_s2d_pad_bwd_nhwc_bf16(const void* ds, void* din, const void* lrelu_ref,
  * dx [b,k], dw [o,k], db [o]: each optional. */
 int esrp_linear_bwd_f32(const float* dy, const float* yout_act, const float* x, const float* w, float* dx, float* dw, float* db,
                         int32_t b, int32_t k, int32_t o, void* stream);
+/* Concurrency helper for layers whose independent launches each fill a fraction of the GPU (the discriminator's deep
+ * layers: 7-70 M-tiles per output-channel slice): n non-blocking side streams owned by the library; fork makes them wait
+ * for everything enqueued on `main` so far, join makes `main` wait for everything enqueued on them. */
+int esrp_streams_create(int32_t n, void** out_streams);
+int esrp_streams_fork(void* main_stream, void* const* sides, int32_t n);
+int esrp_streams_join(void* main_stream, void* const* sides, int32_t n);
 /* nn.Linear (+ optional LeakyReLU 0.2): y[b,o] = sum_k x[b,k] w[o,k] + bias[o]  (architecture.py:122-123). */
 int esrp_linear_f32(const float* x, const float* w, const float* bias, float* y, int32_t b, int32_t k, int32_t o,
                     int32_t act, void* stream);

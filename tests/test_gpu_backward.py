@@ -174,6 +174,8 @@ def test_k4s2_layer_gradients_match_conv2d_autograd(cuda_dev, cin, cout, hw):
     conv = nn.Conv2d(cin, cout, 4, 2, 1).to(cuda_dev)
     eng = DiscriminatorEngine.__new__(DiscriminatorEngine)
     eng.lib, eng.device = _lib.load(), cuda_dev
+    eng._rec = eng._keep = None   # no plan is being recorded: calls run directly
+    eng.nside, eng.side = 0, None  # ... on the current stream
     L = _Layer(conv, None)
     eng._sync(L)
     act = torch.randn(n, hw, hw, cin, device=cuda_dev, generator=g).to(torch.bfloat16)
