@@ -542,7 +542,11 @@ int run_conv1x1_bwd(int nf, const void* x, int x_ctotal, const void* dx2, int d_
                     float* g, const float* extra, float* du_acc, long long npx, cudaStream_t stream) {
   const int sms = sm_count();
   long long tiles = (npx + 63) / 64;
-  int grid = static_cast<int>(tiles < 3LL * sms ? tiles : 3LL * sms);
+  // every CTA ends with 32 x nf atomics into dU: >= 4 tiles per CTA before adding CTAs, at most 3 CTAs per SM
+  long long want = (tiles + 3) / 4;
+  if (want > 3LL * sms) want = 3LL * sms;
+  if (want < 1) want = 1;
+  int grid = static_cast<int>(want);
   if (grid < 1) return 0;
   if (nf == 64)
     conv1x1_bwd_kernel<64><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), x_ctotal,

@@ -356,8 +356,10 @@ int run_wgrad_tc(const WgradLaunch& L, cudaStream_t stream) {
       }
     const int ct = L.bias[i].ctotal;
     const int lanes = 256 / (ct / 8);
-    long long blocks = (L.npx + lanes - 1) / lanes;
+    // every block ends with one atomic per channel: give each pixel lane >= 16 pixels before adding blocks
+    long long blocks = (L.npx + lanes * 16 - 1) / (lanes * 16);
     if (blocks > 4LL * sms) blocks = 4LL * sms;
+    if (blocks < 1) blocks = 1;
     colsum_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(static_cast<const uint4*>(L.bias[i].dy), ct, L.npx, a);
   }
   ESRP_CUDA_OK(cudaGetLastError());
