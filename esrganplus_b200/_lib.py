@@ -73,6 +73,10 @@ class Conv3x3Desc(C.Structure):
         ("pb_ctotal", C.c_int32), ("pb_c0", C.c_int32),
         ("pre_f32", C.c_void_p),
         ("pf_ctotal", C.c_int32), ("pf_c0", C.c_int32),
+        # co-scheduled output slices (row kernel)
+        ("slices", C.c_int32),
+        ("slice_stride", C.c_int64),
+        ("f32_planar", C.c_int32),
     ]
 
 

@@ -98,6 +98,10 @@ class ConvCall:
     pb_c0: int = 0
     pre_f32: Optional[torch.Tensor] = None
     pf_c0: int = 0
+    # co-scheduled output slices (row kernel): slice s uses w_packed / bias + s*slice_stride bytes, channels + s*bn
+    slices: int = 0
+    slice_stride: int = 0
+    f32_planar: int = 0                      # fp32 r1 / r2 / out_f32 are [n,h,c/4,w,4] in memory (include/esrp.h)
     _keep: list = field(default_factory=list, repr=False)
 
     def desc(self) -> Conv3x3Desc:
@@ -155,6 +159,8 @@ class ConvCall:
         if self.pre_f32 is not None:
             assert self.pre_f32.dtype == torch.float32 and self.pre_f32.is_contiguous()
             d.pre_f32, d.pf_ctotal, d.pf_c0 = self.pre_f32.data_ptr(), self.pre_f32.shape[3], self.pf_c0
+        d.slices, d.slice_stride = self.slices, self.slice_stride
+        d.f32_planar = self.f32_planar
         return d
 
     def launch(self) -> None:

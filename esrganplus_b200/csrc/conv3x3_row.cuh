@@ -54,10 +54,12 @@ constexpr int kMaxBlocks = 16;                 // TMEM output-row blocks in the 
 struct SegWalk {
   int u, u_end;
   int img, x0, ya, yb;  // current segment: output rows [ya, yb) of column block x0 of image img
-  __device__ __forceinline__ explicit SegWalk(const ConvKParams& p) {
+  // cta / ncta: position among the CTAs that split the rows (== blockIdx.x / gridDim.x unless the launch
+  // co-schedules output slices, see ConvKParams::nsl)
+  __device__ __forceinline__ SegWalk(const ConvKParams& p, int cta, int ncta) {
     const long long U = p.units_total;
-    u = static_cast<int>(U * blockIdx.x / gridDim.x);
-    u_end = static_cast<int>(U * (blockIdx.x + 1) / gridDim.x);
+    u = static_cast<int>(U * cta / ncta);
+    u_end = static_cast<int>(U * (cta + 1) / ncta);
     img = x0 = ya = yb = 0;
   }
   __device__ __forceinline__ bool next(const ConvKParams& p) {
@@ -152,6 +154,16 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  // Co-scheduled output slices (a 64-channel conv over a K too large for one resident weight set): CTAs
+  // nsl*i .. nsl*i+nsl-1 walk the SAME rows, each with the weights / bias / channel offsets of its own slice.
+  // They run in step on neighbouring SMs, so the input rows come from DRAM once and from L2 afterwards, and
+  // every CTA owns nsl times more rows (half the halo recomputation of nsl separate launches).
+  const int nsl = p.nsl > 1 ? p.nsl : 1;
+  const int sl = nsl > 1 ? static_cast<int>(blockIdx.x) % nsl : 0;
+  const int cta = static_cast<int>(blockIdx.x) / nsl, ncta = static_cast<int>(gridDim.x) / nsl;
+  const int csh = sl * BN;                                  // channel shift of every global channel offset
+  const uint8_t* const w_src = p.w_packed + static_cast<size_t>(sl) * p.sl_stride;
+
   if (warp == kRowEpiWarps && lane == 0) {
     tma_prefetch_desc(&tm0);
     tma_prefetch_desc(&tm1);
@@ -170,7 +182,10 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     tmem_relinquish();
   }
   grid_dep_launch_dependents();
-  if (threadIdx.x < BN) bias_s[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;  // (weights: written long ago)
+  if (threadIdx.x < BN)  // (weights / bias: written long ago)
+    bias_s[threadIdx.x] =
+        p.bias ? reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(p.bias) + static_cast<size_t>(sl) * p.sl_stride)[threadIdx.x]
+               : 0.f;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -200,7 +215,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     if (lane == 0) {
       mbar_arrive_expect_tx(wfull, static_cast<uint32_t>(w_res_bytes));
       for (int c = 0; c < p.num_chunks; ++c)
-        bulk_load_1d(w_res + c * w_chunk_bytes, p.w_packed + static_cast<size_t>(c) * w_chunk_bytes,
+        bulk_load_1d(w_res + c * w_chunk_bytes, w_src + static_cast<size_t>(c) * w_chunk_bytes,
                      w_chunk_bytes, wfull);
       uint32_t tn = 0;
       trace_ev(p, 0, tn);
@@ -210,7 +225,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
       int b = 0;
       uint32_t I = 0, O0 = 0;
       uint8_t* st = stage0;
-      SegWalk sw(p);
+      SegWalk sw(p, cta, ncta);
       while (sw.next(p)) {
         const int r0 = max(sw.ya - 1, 0), r1 = min(sw.yb, p.h - 1);
         for (int r = r0; r <= r1; ++r, ++I) {
@@ -251,7 +266,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     int b = 0;
     uint32_t fph = 0, tph = 0, O0 = 0;
     uint32_t a_lo = a_lo0;
-    SegWalk sw(p);
+    SegWalk sw(p, cta, ncta);
     while (sw.next(p)) {
       const int ni = min(sw.yb, p.h - 1) - max(sw.ya - 1, 0) + 1;
       for (int k = 0; k < ni; ++k) {
@@ -334,7 +349,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     int turn = 0;
     if (threadIdx.x == 0) trace_ev(p, 2, tn);
     grid_dep_wait();  // residual reads / output writes must not race with the previous kernel
-    SegWalk sw(p);
+    SegWalk sw(p, cta, ncta);
     while (sw.next(p)) {
       const int r0 = max(sw.ya - 1, 0), r1 = min(sw.yb, p.h - 1);
       const int xs = sw.x0 + xl;
@@ -350,12 +365,23 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
         const bool real = y >= sw.ya && y < sw.yb && !(p.dbg & ESRP_DBG_NO_EPI);
         const bool store = real && col_ok;
         const uint32_t blk = lane_addr + pos(O) * BN;
-        const size_t pix = (static_cast<size_t>(sw.img) * p.h + (real ? y : sw.ya)) * p.w + (col_ok ? xs : 0);
+        const size_t rowid = static_cast<size_t>(sw.img) * p.h + (real ? y : sw.ya);
+        const size_t pix = rowid * p.w + (col_ok ? xs : 0);
+        // Element offset of channel c (multiple of 4) of this pixel in an fp32 operand of `ct` channels.  NHWC, or
+        // with f32_planar the engine-private [n][h][c/4][w][4] layout: consecutive lanes (pixels) then touch
+        // consecutive 16 bytes, one instruction covers 4 cache lines instead of 32 (the thread == pixel mapping
+        // makes NHWC fp32 accesses cost one LSU wavefront per lane, which bounded conv5).
+        const bool planar = p.f32_planar != 0;
+        const size_t f4_step = planar ? static_cast<size_t>(p.w) : 1;
+        auto off32 = [&](int ct, int c) -> size_t {
+          return planar ? ((rowid * (ct >> 2) + (c >> 2)) * p.w + (col_ok ? xs : 0)) * 4 : pix * ct + c;
+        };
+        auto off_res = [&](int is_f32, int ct, int c) -> size_t { return is_f32 ? off32(ct, c) : pix * ct + c; };
         // residuals of the first round: in flight while we wait for the accumulator
         float r1v[GC], r2v[GC];
-        if (store) {
-          if (p.r1) load_residual<GC>(p.r1, p.r1_is_f32, pix * p.r1_ctotal + p.r1_c0, r1v);
-          if (p.r2) load_residual<GC>(p.r2, p.r2_is_f32, pix * p.r2_ctotal + p.r2_c0, r2v);
+        if (real) {  // every lane (the shuffles of the bf16 store need the whole warp): pix is clamped for columns >= w
+          if (p.r1) load_residual<GC>(p.r1, p.r1_is_f32, off_res(p.r1_is_f32, p.r1_ctotal, p.r1_c0 + csh), r1v, f4_step);
+          if (p.r2) load_residual<GC>(p.r2, p.r2_is_f32, off_res(p.r2_is_f32, p.r2_ctotal, p.r2_c0 + csh), r2v, f4_step);
         }
         mbar_wait(&blk_full[pos(O)], use(O));
         tcgen05_fence_after();
@@ -370,6 +396,8 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
           if (lane == 0) mbar_arrive(&blk_empty[pos(O)]);
           continue;
         }
+        uint32_t pend[8];  // bf16 output of an even round, stored together with the following odd round
+        const bool quad = (ROUNDS % 2 == 0) && (p.cout % (2 * GC) == 0) && !p.no_quad;
         // GC channels per round: load, zero, (after the last round: hand the block back), fused tail, store.
         // The ring is 8-16 blocks deep, so releasing after the last load costs nothing.
 #pragma unroll
@@ -386,7 +414,8 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(&blk_empty[pos(O)]);
           }
-          if (!store || ch0 >= p.cout) continue;
+          if (ch0 >= p.cout) continue;  // (warp-uniform; lanes of columns >= w compute along and store nothing)
+          const int gch = ch0 + csh;  // channel relative to the *_c0 offsets of the descriptor
           float v[GC];
           const float4* bias4 = reinterpret_cast<const float4*>(bias_s + ch0);
 #pragma unroll
@@ -397,7 +426,9 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
             v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b4.z;
             v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b4.w;
           }
-          if constexpr (EXT) ext_mask_store<GC>(p, pix, ch0, v);
+          if constexpr (EXT) {
+            if (store) ext_mask_store<GC>(p, pix, gch, v);
+          }
           if (p.act) {
 #pragma unroll
             for (int i = 0; i < GC; ++i) v[i] = fmaxf(v[i], 0.2f * v[i]);  // LeakyReLU(0.2)
@@ -413,15 +444,15 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
           if (p.r1) {
 #pragma unroll
             for (int i = 0; i < GC; ++i) v[i] = fmaf(p.s1, r1v[i], v[i]);
-            if (g + 1 < ROUNDS) load_residual<GC>(p.r1, p.r1_is_f32, pix * p.r1_ctotal + p.r1_c0 + ch0 + GC, r1v);
+            if (g + 1 < ROUNDS) load_residual<GC>(p.r1, p.r1_is_f32, off_res(p.r1_is_f32, p.r1_ctotal, p.r1_c0 + gch + GC), r1v, f4_step);
           }
           if constexpr (EXT) {
             if (p.r2 && p.r2_pre) {
 #pragma unroll
               for (int i = 0; i < GC; ++i) v[i] += r2v[i];
-              if (g + 1 < ROUNDS) load_residual<GC>(p.r2, p.r2_is_f32, pix * p.r2_ctotal + p.r2_c0 + ch0 + GC, r2v);
+              if (g + 1 < ROUNDS) load_residual<GC>(p.r2, p.r2_is_f32, off_res(p.r2_is_f32, p.r2_ctotal, p.r2_c0 + gch + GC), r2v, f4_step);
             }
-            ext_pre_and_mask<GC>(p, pix, ch0, v);
+            if (store) ext_pre_and_mask<GC>(p, pix, gch, v);
           }
           if (p.noise) {
             const unsigned long long nseed = p.seed_ptr ? __ldg(p.seed_ptr) : p.seed;  // graph replays read the key from memory
@@ -429,7 +460,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
             for (int i = 0; i < GC; i += 4) {
               float z[4];
               philox_normal4(nseed,
-                             p.offset + (pix * static_cast<unsigned long long>(p.noise_ctotal) + p.noise_c0 + ch0 + i) / 4, z);
+                             p.offset + (pix * static_cast<unsigned long long>(p.noise_ctotal) + p.noise_c0 + gch + i) / 4, z);
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj) {
 #pragma unroll
@@ -444,28 +475,65 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
           } else if (p.r2) {
 #pragma unroll
             for (int i = 0; i < GC; ++i) v[i] = fmaf(p.s2, v[i], r2v[i]);
-            if (g + 1 < ROUNDS) load_residual<GC>(p.r2, p.r2_is_f32, pix * p.r2_ctotal + p.r2_c0 + ch0 + GC, r2v);
+            if (g + 1 < ROUNDS) load_residual<GC>(p.r2, p.r2_is_f32, off_res(p.r2_is_f32, p.r2_ctotal, p.r2_c0 + gch + GC), r2v, f4_step);
           }
           if (p.out_bf16) {
-            uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.ob_ctotal + p.ob_c0 + ch0);
+            uint32_t pk[GC / 2];
 #pragma unroll
-            for (int i = 0; i < GC / 8; ++i) {
-              uint32_t pk[4];
+            for (int i = 0; i < GC / 2; ++i) {
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+              pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            if (!quad) {
+              if (store) {
+                uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.ob_ctotal + p.ob_c0 + gch);
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * i + 2 * jj], v[8 * i + 2 * jj + 1]);
-                pk[jj] = *reinterpret_cast<const uint32_t*>(&h2);
+                for (int i = 0; i < GC / 8; ++i)  // next conv's operand: keep in L2
+                  st_global_u4_hint(op + i, make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]), kL2EvictLast);
               }
-              st_global_u4_hint(op + i, make_uint4(pk[0], pk[1], pk[2], pk[3]), kL2EvictLast);  // next conv's operand
+            } else if ((g & 1) == 0) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pend[i] = pk[i];
+            } else {
+              // 32 channels = four 16-byte chunks per pixel.  Stored by their owner, one instruction touches 32 cache
+              // lines (pixel stride = ob_ctotal * 2 bytes); after a 4x4 transpose inside each group of four lanes,
+              // lane j holds chunk j of the group's four pixels and an instruction writes 8 x 64 contiguous bytes.
+              const bool hi = (lane & 2) != 0, lo = (lane & 1) != 0;
+              uint32_t d0[8], d1[8];  // [pixel hi bit][chunk lo bit][4 words] after the exchange with lane ^ 2
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const uint32_t snd = hi ? pend[i] : pk[i], kp = hi ? pk[i] : pend[i];
+                const uint32_t rc = __shfl_xor_sync(0xffffffffu, snd, 2);
+                d0[i] = hi ? rc : kp;
+                d1[i] = hi ? kp : rc;
+              }
+              uint32_t e[4][4];       // [pixel of the group][4 words] after the exchange with lane ^ 1
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint32_t s0_ = lo ? d0[i] : d0[4 + i], k0_ = lo ? d0[4 + i] : d0[i];
+                const uint32_t s1_ = lo ? d1[i] : d1[4 + i], k1_ = lo ? d1[4 + i] : d1[i];
+                const uint32_t r0_ = __shfl_xor_sync(0xffffffffu, s0_, 1), r1_ = __shfl_xor_sync(0xffffffffu, s1_, 1);
+                e[0][i] = lo ? r0_ : k0_;
+                e[1][i] = lo ? k0_ : r0_;
+                e[2][i] = lo ? r1_ : k1_;
+                e[3][i] = lo ? k1_ : r1_;
+              }
+              const int xg = sw.x0 + q * 32 + (lane & ~3);  // first pixel of this lane's group
+              __nv_bfloat16* ob = p.out_bf16 + (rowid * p.w + xg) * p.ob_ctotal + p.ob_c0 + (gch - GC) + (lane & 3) * 8;
+#pragma unroll
+              for (int m = 0; m < 4; ++m)
+                if (xg + m < p.w)
+                  st_global_u4_hint(reinterpret_cast<uint4*>(ob + static_cast<size_t>(m) * p.ob_ctotal),
+                                    make_uint4(e[m][0], e[m][1], e[m][2], e[m][3]), kL2EvictLast);
             }
           }
-          if (p.out_f32) {
-            float4* op = reinterpret_cast<float4*>(p.out_f32 + pix * p.of_ctotal + p.of_c0 + ch0);
+          if (p.out_f32 && store) {
+            float4* op = reinterpret_cast<float4*>(p.out_f32 + off32(p.of_ctotal, p.of_c0 + gch));
 #pragma unroll
             for (int i = 0; i < GC / 4; ++i)  // fp32 trunk: read once, a whole dense block later -> stream
-              st_global_f4_hint(op + i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), kL2EvictFirst);
+              st_global_f4_hint(op + i * f4_step, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), kL2EvictFirst);
           }
-          if (p.out_nchw) {
+          if (p.out_nchw && store) {
             const size_t plane = static_cast<size_t>(p.h) * p.w;
             float* op = p.out_nchw + (static_cast<size_t>(sw.img) * p.cout) * plane + static_cast<size_t>(y) * p.w + xs;
 #pragma unroll

@@ -85,12 +85,13 @@ struct TileWalk {
 
 // GC consecutive values of a residual tensor (fp32 or bf16 storage) into fp32 registers.
 template <int GC>
-__device__ __forceinline__ void load_residual(const void* base, int is_f32, size_t elem_off, float (&r)[GC]) {
+__device__ __forceinline__ void load_residual(const void* base, int is_f32, size_t elem_off, float (&r)[GC],
+                                              size_t f4_step = 1) {  // fp32: distance between consecutive float4s
   if (is_f32) {
     const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(base) + elem_off);
 #pragma unroll
     for (int i = 0; i < GC / 4; ++i) {
-      const float4 t = ld_global_f4_hint(rp + i, kL2EvictFirst);  // fp32 trunk: streamed, do not displace bf16 operands
+      const float4 t = ld_global_f4_hint(rp + i * f4_step, kL2EvictFirst);  // fp32 trunk: streamed, do not displace bf16 operands
       r[4 * i] = t.x; r[4 * i + 1] = t.y; r[4 * i + 2] = t.z; r[4 * i + 3] = t.w;
     }
   } else {

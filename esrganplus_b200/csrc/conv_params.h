@@ -56,6 +56,10 @@ struct ConvKParams {
   int pb_ctotal, pb_c0;
   float* pre_f32;
   int pf_ctotal, pf_c0;
+  int nsl;                 // > 1: the launch co-schedules nsl output slices of bn channels (row kernel only)
+  long long sl_stride;     // bytes from one slice's packed weights (and bias) to the next
+  int f32_planar;          // fp32 operands (r1/r2/out_f32) are [n][h][c/4][w][4] instead of NHWC (row kernel only)
+  int no_quad;             // row kernel: store bf16 outputs pixel by pixel (timing experiments: ESRP_NO_QUAD)
   int dbg;           // timing experiments only (ESRP_DBG_*): results are wrong when non-zero
   long long* trace;  // optional [3][1024] clock64 timeline of CTA 0 (see trace_ev)
 };

@@ -137,6 +137,17 @@ int plan_conv(const esrp_conv3x3_t& d, ConvLaunch* out) {
   if (d.mask_in && ((d.mask_in_ctotal % 16) || (d.mask_in_c0 % 16) || (d.cout % 16))) return set_error("conv3x3: mask_in needs 16-bit aligned channel ranges");
   if (d.pre_bf16 && ((d.pb_ctotal % 8) || (d.pb_c0 % 8) || (d.cout % 16))) return set_error("conv3x3: pre_bf16 channel alignment");
   if (d.pre_f32 && ((d.pf_ctotal % 4) || (d.pf_c0 % 4) || (d.cout % 16))) return set_error("conv3x3: pre_f32 channel alignment");
+  if (d.slices > 1) {
+    if (d.w_layout != ESRP_LAYOUT_ROW) return set_error("conv3x3: slices > 1 needs ESRP_LAYOUT_ROW weights");
+    if (d.slices > 4 || d.cout != d.bn) return set_error("conv3x3: slices=%d needs cout == bn and at most 4 slices", d.slices);
+    if (d.out_nchw) return set_error("conv3x3: slices > 1 cannot write out_nchw");
+    if (d.slice_stride <= 0 || (d.slice_stride % 16)) return set_error("conv3x3: slice_stride must be a positive multiple of 16 bytes");
+  }
+  if (d.f32_planar) {
+    if (d.w_layout != ESRP_LAYOUT_ROW || ext) return set_error("conv3x3: f32_planar needs ESRP_LAYOUT_ROW weights and no training extensions");
+    if ((d.r1 && d.r1_is_f32 && ((d.r1_ctotal | d.r1_c0) % 4)) || (d.r2 && d.r2_is_f32 && ((d.r2_ctotal | d.r2_c0) % 4)))
+      return set_error("conv3x3: f32_planar channel alignment");
+  }
   if (d.w_layout == ESRP_LAYOUT_ROW) return ext ? plan_row_ext(d, out) : plan_row_base(d, out);
   if (d.w_layout != ESRP_LAYOUT_TILE) return set_error("conv3x3: unknown w_layout=%d", d.w_layout);
   return ext ? plan_tile_ext(d, out) : plan_tile_base(d, out);

@@ -24,6 +24,9 @@ void copy_common(const esrp_conv3x3_t& d, ConvKParams* pp) {
   p.out_bf16 = static_cast<__nv_bfloat16*>(d.out_bf16); p.ob_ctotal = d.ob_ctotal; p.ob_c0 = d.ob_c0;
   p.out_f32 = static_cast<float*>(d.out_f32); p.of_ctotal = d.of_ctotal; p.of_c0 = d.of_c0;
   p.out_nchw = d.out_nchw;
+  p.nsl = d.slices > 1 ? d.slices : 1;
+  p.sl_stride = d.slices > 1 ? d.slice_stride : 0;
+  p.f32_planar = d.f32_planar;
   p.trace = static_cast<long long*>(d.trace);
   p.dbg = d.variant & 0x1F00;
   p.mask_out = static_cast<unsigned short*>(d.mask_out); p.mo_ctotal = d.mask_out_ctotal; p.mo_c0 = d.mask_out_c0;

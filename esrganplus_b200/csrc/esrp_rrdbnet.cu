@@ -248,6 +248,24 @@ void base_desc(const Rrdbnet* m, const ConvW& c, int n, int h, int w, esrp_conv3
   d->sigma = 0.1f;
 }
 
+// Timing experiments: ESRP_NO_COSLICE=1 issues the output slices of a wide conv as separate launches again.
+bool no_coslice() {
+  static const bool off = getenv("ESRP_NO_COSLICE") != nullptr;
+  return off;
+}
+
+// Turn the descriptor of slice `c` into ONE launch over `nsl` consecutive slices (esrp_conv3x3_t::slices): their
+// packed weights and biases sit at a constant stride in the weight buffer (rrdbnet_create allocates them back to back).
+int coslice(const ConvW& c, const ConvW& next, int nsl, esrp_conv3x3_t* d) {
+  const long long stride = static_cast<long long>(next.w_off) - static_cast<long long>(c.w_off);
+  if (stride <= 0 || static_cast<long long>(next.b_off) - static_cast<long long>(c.b_off) != stride || next.bn != c.bn ||
+      next.row0 != c.row0 + c.bn || c.rows != c.bn)
+    return set_error("rrdbnet: conv slices are not laid out at a constant stride");
+  d->slices = nsl;
+  d->slice_stride = stride;
+  return 0;
+}
+
 namespace {
 
 struct Workspace {
@@ -302,6 +320,10 @@ int build_plan(Rrdbnet* m, int n, int h, int w, uint8_t* wsp, int training, cuda
       if (c.layout != lay && pack_one(m, &c, lay, stream)) return 1;
     return 0;
   };
+  // The fp32 twin of the trunk is only ever touched by conv epilogues of this plan: where they all run on the row
+  // kernel (thread == pixel) it is kept as [n][h][c/4][w][4] so that its reads / writes coalesce (esrp_conv3x3_t::f32_planar).
+  static const bool no_planar = getenv("ESRP_NO_PLANAR") != nullptr;  // timing experiments
+  const int planar = (layout_for_width(w) == ESRP_LAYOUT_ROW && !no_planar) ? 1 : 0;
   // plain single-source conv (all slices): src -> [bf16 out][f32 out][nchw out], optional fp32 residual
   auto plain = [&](std::vector<ConvW>& cs, int hh, int ww, const void* src, int src_ct, int act, void* out_b,
                    void* out_f, const void* r1_f32, bool to_y) -> int {
@@ -315,6 +337,7 @@ int build_plan(Rrdbnet* m, int n, int h, int w, uint8_t* wsp, int training, cuda
       if (r1_f32) { d.r1 = r1_f32; d.r1_is_f32 = 1; d.r1_ctotal = c.cout; d.r1_c0 = c.row0; d.s1 = 1.f; }
       if (out_b) { d.out_bf16 = out_b; d.ob_ctotal = c.cout; d.ob_c0 = c.row0; }
       if (out_f) { d.out_f32 = out_f; d.of_ctotal = c.cout; d.of_c0 = c.row0; }
+      if (r1_f32 || out_f) d.f32_planar = planar;
       if (to_y) d.out_nchw = reinterpret_cast<float*>(wsp);  // placeholder, patched per call
       if (push_conv(d, to_y)) return 1;
     }
@@ -352,10 +375,13 @@ int build_plan(Rrdbnet* m, int n, int h, int w, uint8_t* wsp, int training, cuda
       uint8_t* out_f = wsp + ws.tf[slot];
       uint8_t* G = wsp + ws.g;
       const bool wide5 = !m->rdb5w.empty() && layout_for_width(w) == ESRP_LAYOUT_TILE;
-      for (int k = 0; k < (wide5 ? 5 : m->per_rdb); ++k) {
+      // row kernel: the conv5 slices (32 output channels each) share one launch, CTA pairs walk the same rows
+      const int nsl5 = (!wide5 && m->per_rdb > 5 && !no_coslice()) ? m->per_rdb - 4 : 1;
+      for (int k = 0; k < ((wide5 || nsl5 > 1) ? 5 : m->per_rdb); ++k) {
         const ConvW& c = (wide5 && k == 4) ? m->rdb5w[static_cast<size_t>(i) * 3 + r]
                                            : m->rdb[(static_cast<size_t>(i) * 3 + r) * m->per_rdb + k];
         base_desc(m, c, n, h, w, &d);
+        if (k == 4 && nsl5 > 1 && coslice(c, (&c)[1], nsl5, &d)) return 1;
         d.src[0] = cur_b; d.src_ctotal[0] = nf;
         d.src[1] = G; d.src_ctotal[1] = 4 * gc;
         for (int ch = 0; ch < c.num_chunks; ++ch) {
@@ -383,6 +409,7 @@ int build_plan(Rrdbnet* m, int n, int h, int w, uint8_t* wsp, int training, cuda
           }
           d.out_bf16 = out_b; d.ob_ctotal = nf; d.ob_c0 = c0;
           d.out_f32 = out_f; d.of_ctotal = nf; d.of_c0 = c0;
+          d.f32_planar = planar;
           if (push_conv(d, false, training != 0, noise_index)) return 1;
         }
       }

@@ -78,6 +78,9 @@ int ensure_layouts(Rrdbnet* m, int w, cudaStream_t s);
 // fill the common part of a conv descriptor from packed weights
 void base_desc(const Rrdbnet* m, const ConvW& c, int n, int h, int w, esrp_conv3x3_t* d);
 void destroy_train_state(Rrdbnet* m);
+// co-scheduled output slices of a wide conv (esrp_conv3x3_t::slices), esrp_rrdbnet.cu
+bool no_coslice();
+int coslice(const ConvW& c, const ConvW& next, int nsl, esrp_conv3x3_t* d);
 
 template <class F>
 int for_each_conv(Rrdbnet* m, F&& f) {

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/esrp.h"
@@ -51,6 +52,8 @@ static int plan_row_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
   p.tmem_cols = 512;
   out->smem = kSmemFixed + 1024 + w_all + p.stages * row_bytes;
   copy_common(d, &p);
+  static const bool no_quad = getenv("ESRP_NO_QUAD") != nullptr;
+  p.no_quad = no_quad ? 1 : 0;
   if (make_nhwc_tmap(&out->tm0, d.src[0], d.n, d.h, d.w, d.src_ctotal[0], KC, kRowTile + 2, 1)) return 1;
   if (d.src[1]) {
     if (make_nhwc_tmap(&out->tm1, d.src[1], d.n, d.h, d.w, d.src_ctotal[1], KC, kRowTile + 2, 1)) return 1;
@@ -67,7 +70,9 @@ static int plan_row_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
   out->threads = kRowThreads;
   const int sms = sm_count();
   if (sms <= 0) return set_error("conv3x3: no CUDA device");
-  out->grid = p.units_total < sms ? static_cast<int>(p.units_total) : sms;
+  // co-scheduled slices: groups of nsl CTAs share a row range
+  const int groups = sms / p.nsl < 1 ? 1 : sms / p.nsl;
+  out->grid = (p.units_total < groups ? static_cast<int>(p.units_total) : groups) * p.nsl;
   return 0;
 }
 

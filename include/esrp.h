@@ -112,6 +112,20 @@ typedef struct esrp_conv3x3 {
   int32_t pb_ctotal, pb_c0;
   void* pre_f32;                /* NHWC fp32 copy of v before mask_in/noise/s2, or NULL       */
   int32_t pf_ctotal, pf_c0;
+  /* ---- co-scheduled output slices (optional; 0 or 1 = off; ESRP_LAYOUT_ROW only) ----
+   * slices = S > 1: ONE launch computes S consecutive slices of bn output channels of the same conv
+   * (a 64-channel conv whose K is too large for one resident weight set, e.g. conv5 of a dense block,
+   * block.py:258).  Slice s uses w_packed + s*slice_stride and bias + s*slice_stride (bytes) and adds
+   * s*bn to every channel offset (ob_c0, of_c0, r1_c0, r2_c0, noise_c0, mask_*_c0, pb_c0, pf_c0).
+   * CTAs S*i..S*i+S-1 walk the same image rows, so the input is fetched from HBM once. */
+  int32_t slices;
+  int64_t slice_stride;
+  /* ---- layout of the fp32 operands (optional; ESRP_LAYOUT_ROW, no training extensions) ----
+   * 0: r1 / r2 / out_f32 (where fp32) are NHWC [n,h,w,c].  1: they are [n,h,c/4,w,4] ("planar"): the
+   * row kernel maps one thread to one pixel, so a warp then reads / writes 512 contiguous bytes per
+   * instruction.  Private to a caller that owns both producer and consumer of the tensor (the
+   * engine's fp32 residual trunk); channel counts / offsets must be multiples of 4. */
+  int32_t f32_planar;
 } esrp_conv3x3_t;
 
 const char* esrp_last_error(void);

@@ -168,6 +168,86 @@ def test_conv3x3_output_channel_slices_and_transposed_pack(cuda_dev, layout):
     assert (out2.permute(0, 3, 1, 2) - ref2).abs().max().item() <= 2e-3 * max(1.0, ref2.abs().max().item())
 
 
+@pytest.mark.parametrize("shape", [(2, 20, 200), (3, 37, 130), (1, 1, 128), (16, 128, 128)])
+@pytest.mark.parametrize("train_ext", [False, True])
+def test_conv3x3_coscheduled_slices(cuda_dev, shape, train_ext):
+    """conv5 of a dense block (block.py:258,268; RRDB skip block.py:291) as ONE launch over two 32-channel output
+    slices (esrp_conv3x3_t::slices): same arithmetic as two launches, so the results must be bit-identical to them,
+    and within the single-conv tolerance of torch conv2d."""
+    n, h, w = shape
+    g = torch.Generator(device=cuda_dev).manual_seed(1234 + w)
+    t_in = torch.randn(n, h, w, 64, device=cuda_dev, generator=g).to(torch.bfloat16)
+    gro = torch.randn(n, h, w, 128, device=cuda_dev, generator=g).to(torch.bfloat16)
+    chunks = [(0, 0), (1, 0), (1, 64)]
+    wt = torch.randn(64, 192, 3, 3, device=cuda_dev, generator=g) / (192 * 9) ** 0.5
+    bias = torch.randn(64, device=cuda_dev, generator=g)
+    lib = _lib.load()
+    nbytes = lib.esrp_packed_conv3x3_bytes(3, 64, 32, 0)
+    w_al = (nbytes + 1023) // 1024 * 1024
+    stride = w_al + 1024
+    buf = torch.zeros(2 * stride, dtype=torch.uint8, device=cuda_dev)
+    biases = []
+    for sl in (0, 1):
+        K.pack_conv3x3_weights(wt, 64, 32, [0, 64, 128], row0=32 * sl, rows=32, layout=_lib.LAYOUT_ROW,
+                               out=buf[sl * stride: sl * stride + nbytes])
+        b = buf[sl * stride + w_al: sl * stride + w_al + 128].view(torch.float32)
+        b.copy_(bias[32 * sl: 32 * sl + 32])
+        biases.append(b)
+    r1 = torch.randn(n, h, w, 64, device=cuda_dev, generator=g)
+    r2 = torch.randn(n, h, w, 64, device=cuda_dev, generator=g)
+
+    def run(sliced):
+        ob = torch.zeros((n, h, w, 64), device=cuda_dev, dtype=torch.bfloat16)
+        of = torch.zeros((n, h, w, 64), device=cuda_dev)
+        pre = torch.zeros((n, h, w, 64), device=cuda_dev) if train_ext else None
+        common = dict(n=n, h=h, w=w, srcs=[t_in, gro], kc=64, chunks=chunks, bn=32, cout=32, w_layout=_lib.LAYOUT_ROW,
+                      s0=0.2, r1=r1, s1=1.0, r2=r2, s2=0.2, out_bf16=ob, out_f32=of, noise=1, noise_ctotal=64, seed=77,
+                      offset=5 << 36, pre_f32=pre)
+        if sliced:
+            K.ConvCall(w_packed=buf[:nbytes], bias=biases[0], slices=2, slice_stride=stride, **common).launch()
+        else:
+            for sl in (0, 1):
+                K.ConvCall(w_packed=buf[sl * stride: sl * stride + nbytes], bias=biases[sl], r1_c0=32 * sl, r2_c0=32 * sl,
+                           ob_c0=32 * sl, of_c0=32 * sl, noise_c0=32 * sl, pf_c0=32 * sl, **common).launch()
+        return ob, of, pre
+
+    ob1, of1, pre1 = run(True)
+    ob2, of2, pre2 = run(False)
+    assert torch.equal(of1, of2) and torch.equal(ob1, ob2)
+    if not train_ext:
+        # fp32 operands in the engine-private [n,h,c/4,w,4] layout (esrp_conv3x3_t::f32_planar): same values
+        def to_planar(t):
+            return t.view(n, h, w, 16, 4).permute(0, 1, 3, 2, 4).contiguous().view(n, h, w, 64)
+
+        def from_planar(t):
+            return t.view(n, h, 16, w, 4).permute(0, 1, 3, 2, 4).contiguous().view(n, h, w, 64)
+
+        ob3 = torch.zeros_like(ob1)
+        of3 = torch.zeros_like(of1)
+        K.ConvCall(n=n, h=h, w=w, srcs=[t_in, gro], kc=64, chunks=chunks, bn=32, cout=32, w_layout=_lib.LAYOUT_ROW, s0=0.2,
+                   r1=to_planar(r1), s1=1.0, r2=to_planar(r2), s2=0.2, out_bf16=ob3, out_f32=of3, noise=1, noise_ctotal=64,
+                   seed=77, offset=5 << 36, w_packed=buf[:nbytes], bias=biases[0], slices=2, slice_stride=stride,
+                   f32_planar=1).launch()
+        assert torch.equal(ob3, ob1) and torch.equal(from_planar(of3), of1)
+    if train_ext:
+        assert torch.equal(pre1, pre2)
+    # against torch: v = 0.2*conv + r1; noise; 0.2*v + r2  (draws regenerated on the host, DESIGN.md 4.3)
+    ref = _ref_conv([t_in, gro], chunks, 64, wt, bias, act=0)
+    v = (0.2 * ref + r1.permute(0, 3, 1, 2)).permute(0, 2, 3, 1).contiguous()
+    if train_ext:
+        scale = max(1.0, v.abs().max().item())
+        assert (pre1 - v).abs().max().item() <= 2e-3 * scale
+    if n * h * w <= 20000:
+        z = np.empty(n * h * w * 64, dtype=np.float32)
+        _lib.check(lib.esrp_philox_normal_host(77, 5 << 36, z.size, z.ctypes.data), "philox")
+        zt = torch.from_numpy(z).view(n, h, w, 64).to(cuda_dev)
+        v = v + zt * 0.1 * v
+        v = 0.2 * v + r2
+        scale = max(1.0, v.abs().max().item())
+        assert (of1 - v).abs().max().item() <= 2e-3 * scale
+        assert (ob1.float() - v).abs().max().item() <= 1e-2 * scale
+
+
 def test_conv3x3_rejects_bad_arguments(cuda_dev):
     s0 = torch.zeros(1, 8, 8, 64, device=cuda_dev, dtype=torch.bfloat16)
     wp = torch.zeros(9 * 32 * 64 * 2, device=cuda_dev, dtype=torch.uint8)  # 3 ky x 96 rows x 64 ch bf16
