@@ -63,9 +63,14 @@ int make_nhwc_tmap(CUtensorMap* tm, const void* ptr, int n, int h, int w, int c_
   cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUtensorMapSwizzle sw = (kc == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  // L2 promotion: a miss fetches 256 contiguous bytes only where the box covers the whole pixel (its rows are then
+  // contiguous in memory).  A 64-channel chunk of the 128-channel growth buffer is 128 of every 256 bytes: with 256-byte
+  // promotion conv2 / conv3 pulled the unused half of G from DRAM as well (ncu: 104-107 MB read for 74 MB of operands).
+  static const bool promo256 = getenv("ESRP_TMAP_PROMO256") != nullptr;  // timing experiments
+  const CUtensorMapL2promotion promo = (kc == c_total || promo256) ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                       : (kc * 2 >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_64B);
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error("cuTensorMapEncodeTiled failed (%d) ptr=%p nhwc=(%d,%d,%d,%d) kc=%d box=(%d,%d)",
                      (int)r, ptr, n, h, w, c_total, kc, box_w, box_h);

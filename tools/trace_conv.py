@@ -52,6 +52,8 @@ def run(name, n=16, h=128, w=128, variant=0, iters=50):
     us = e0.elapsed_time(e1) * 1000 / iters
     flops = 2.0 * n * h * w * cout * 9 * cin
     print(f"## {name} variant={variant}: {us:.1f} us  {flops / us * 1e-6:.0f} TFLOP/s")
+    if variant & 0x1F00:  # timing experiments (ESRP_DBG_*): no timeline
+        return
     call.trace = tr
     call.launch()
     torch.cuda.synchronize()
