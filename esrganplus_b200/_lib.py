@@ -77,6 +77,7 @@ class Conv3x3Desc(C.Structure):
         ("slices", C.c_int32),
         ("slice_stride", C.c_int64),
         ("f32_planar", C.c_int32),
+        ("k_valid", C.c_int32),
     ]
 
 

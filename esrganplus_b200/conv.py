@@ -102,6 +102,7 @@ class ConvCall:
     slices: int = 0
     slice_stride: int = 0
     f32_planar: int = 0                      # fp32 r1 / r2 / out_f32 are [n,h,c/4,w,4] in memory (include/esrp.h)
+    k_valid: int = 0                         # input channels that carry non-zero weights (0 = all)
     _keep: list = field(default_factory=list, repr=False)
 
     def desc(self) -> Conv3x3Desc:
@@ -161,6 +162,7 @@ class ConvCall:
             d.pre_f32, d.pf_ctotal, d.pf_c0 = self.pre_f32.data_ptr(), self.pre_f32.shape[3], self.pf_c0
         d.slices, d.slice_stride = self.slices, self.slice_stride
         d.f32_planar = self.f32_planar
+        d.k_valid = self.k_valid
         return d
 
     def launch(self) -> None:

@@ -89,7 +89,7 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[GC]) 
 // WRAP = false is the straight-line common case (one N = 3*BN MMA per tap, compile-time descriptors: the
 // issue sequence must stay at ~2 integer ops per MMA because the tensor pipe queues almost nothing);
 // WRAP = true splits every tap in two narrower MMAs where the three blocks straddle the end of the ring.
-template <int KC, int BN, int MW, bool WRAP>
+template <int KC, int BN, int MW, bool WRAP, int KSN = KC / 16>  // KSN: K-slices of 16 channels to issue (the rest: zero weights)
 __device__ __forceinline__ void issue_taps(uint32_t dA, uint32_t dB, uint32_t idA, uint32_t idB, uint32_t bB,
                                            uint32_t al, uint32_t bl, uint32_t desc_hi, uint32_t w_block_desc) {
   constexpr int RB = KC * 2, KS = KC / 16;
@@ -97,7 +97,7 @@ __device__ __forceinline__ void issue_taps(uint32_t dA, uint32_t dB, uint32_t id
 #pragma unroll
   for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
+    for (int ks = 0; ks < KSN; ++ks) {
       const bool warp0 = kx == 1 || (kx == 0 && ks < KS / 2);
       if (warp0 != (MW == 0)) continue;
       const uint32_t a_d = al + ((kx * RB + ks * 32) >> 4);  // the 130-pixel row shifted by kx pixels
@@ -264,7 +264,9 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     uint32_t tn = 0;
     if (mw == 0 && lane == 0) trace_ev(p, 1, tn);
     int b = 0;
-    uint32_t fph = 0, tph = 0, O0 = 0;
+    uint32_t fph = 0, tph = 0, O0 = 0, I = 0;
+    const bool alt = p.row_alt != 0;
+    const int nfull = p.last_half ? nch - 1 : nch;  // chunks issued over all of their K-slices
     uint32_t a_lo = a_lo0;
     SegWalk sw(p, cta, ncta);
     while (sw.next(p)) {
@@ -290,6 +292,63 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
         // The issuers take strict turns (warp 0, warp 1, warp 0, ...): left alone they fall into lock-step
         // (both wait, both issue interleaved, both commit) and their per-row overhead is exposed; in turns,
         // the waits / commits of one warp overlap the MMAs of the other.
+        if (alt) {
+          // Row-alternating issue: warp (I & 1) issues ALL taps of input row I, then passes the turn: one hand-over
+          // per row instead of two, and a whole row of MMAs hides the other warp's waits / commits.  A block still
+          // collects two commits: one from the issuer of the row that completes it ("final", after row r+1) and one
+          // from the issuer of its middle row r (commits only track the committing thread's MMAs; rows r-1 and r+1
+          // belong to the same warp).  Segment ends: the missing contributor's commit is issued by the same thread.
+          if ((I & 1u) == static_cast<uint32_t>(mw)) {
+            mbar_wait(&tok[mw], tph ^ (mw == 0 ? 1u : 0u));
+            if (elect_one()) {
+              uint32_t al = a_lo, bl = w_lo0;
+              for (int c = 0; c < nfull; ++c, al += chunk_step, bl += w_step) {
+                if (nB == 0) {
+                  issue_taps<KC, BN, 0, false>(dA, dB, idA, idB, bB, al, bl, DESC_HI, w_block_desc);
+                  issue_taps<KC, BN, 1, false>(dA, dB, idA, idB, bB, al, bl, DESC_HI, w_block_desc);
+                } else {
+                  issue_taps<KC, BN, 0, true>(dA, dB, idA, idB, bB, al, bl, DESC_HI, w_block_desc);
+                  issue_taps<KC, BN, 1, true>(dA, dB, idA, idB, bB, al, bl, DESC_HI, w_block_desc);
+                }
+              }
+              if (nfull < nch) {  // last chunk: only its first half carries weights (K = 96 / 160 in 64-channel chunks)
+                if (nB == 0) {
+                  issue_taps<KC, BN, 0, false, KS / 2>(dA, dB, idA, idB, bB, al, bl, DESC_HI, w_block_desc);
+                  issue_taps<KC, BN, 1, false, KS / 2>(dA, dB, idA, idB, bB, al, bl, DESC_HI, w_block_desc);
+                } else {
+                  issue_taps<KC, BN, 0, true, KS / 2>(dA, dB, idA, idB, bB, al, bl, DESC_HI, w_block_desc);
+                  issue_taps<KC, BN, 1, true, KS / 2>(dA, dB, idA, idB, bB, al, bl, DESC_HI, w_block_desc);
+                }
+              }
+              if (AUX) {
+                al = a_lo;
+                bl = w_lo0;
+                for (int c = 0; c < naux; ++c, al += chunk_step, bl += w_step) {
+#pragma unroll
+                  for (int ks = 0; ks < KS; ++ks)
+                    umma_f16_ss2(d_aux, al + ((1 * RB + ks * 32) >> 4), DESC_HI,
+                                 bl + w_block_desc + ((3 * BN * RB + ks * 32) >> 4), DESC_HI, idesc_aux,
+                                 (c | ks) != 0 ? 1u : 0u);
+                }
+              }
+              mbar_arrive(&tok[mw ^ 1]);                // the other warp's turn
+              umma_commit(&blk_full[pos(O0 + k)]);      // final contributor of output row r-1
+              umma_commit(&blk_full[pos(O0 + k + 1)]);  // middle contributor of output row r
+              if (k == 0) umma_commit(&blk_full[pos(O0)]);  // (dummy) first block: no earlier row
+              if (k == ni - 1) {                        // last input row of the segment: no later row
+                umma_commit(&blk_full[pos(O0 + k + 1)]);
+                umma_commit(&blk_full[pos(O0 + k + 2)]);
+                umma_commit(&blk_full[pos(O0 + k + 2)]);
+              }
+            }
+            __syncwarp();
+            tph ^= 1;
+          }
+          ++I;
+          a_lo += row_step;
+          if (++b == D) { b = 0; fph ^= 1; a_lo = a_lo0; }
+          continue;
+        }
         mbar_wait(&tok[mw], tph ^ (mw == 0 ? 1u : 0u));
         if (elect_one()) {
           uint32_t al = a_lo, bl = w_lo0;

@@ -59,6 +59,8 @@ struct ConvKParams {
   int nsl;                 // > 1: the launch co-schedules nsl output slices of bn channels (row kernel only)
   long long sl_stride;     // bytes from one slice's packed weights (and bias) to the next
   int f32_planar;          // fp32 operands (r1/r2/out_f32) are [n][h][c/4][w][4] instead of NHWC (row kernel only)
+  int last_half;           // row kernel (row_alt): only the first kc/2 channels of the last chunk carry weights
+  int row_alt;             // row kernel: the two MMA issuers alternate whole rows instead of splitting the taps of every row
   int no_quad;             // row kernel: store bf16 outputs pixel by pixel (timing experiments: ESRP_NO_QUAD)
   int dbg;           // timing experiments only (ESRP_DBG_*): results are wrong when non-zero
   long long* trace;  // optional [3][1024] clock64 timeline of CTA 0 (see trace_ev)

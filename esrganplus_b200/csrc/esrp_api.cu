@@ -148,6 +148,8 @@ int plan_conv(const esrp_conv3x3_t& d, ConvLaunch* out) {
     if (d.out_nchw) return set_error("conv3x3: slices > 1 cannot write out_nchw");
     if (d.slice_stride <= 0 || (d.slice_stride % 16)) return set_error("conv3x3: slice_stride must be a positive multiple of 16 bytes");
   }
+  if (d.k_valid < 0 || d.k_valid > d.num_chunks * d.kc || (d.k_valid > 0 && d.k_valid <= (d.num_chunks - 1) * d.kc))
+    return set_error("conv3x3: k_valid=%d must lie in the last of the %d chunks of %d channels", d.k_valid, d.num_chunks, d.kc);
   if (d.f32_planar) {
     if (d.w_layout != ESRP_LAYOUT_ROW || ext) return set_error("conv3x3: f32_planar needs ESRP_LAYOUT_ROW weights and no training extensions");
     if ((d.r1 && d.r1_is_f32 && ((d.r1_ctotal | d.r1_c0) % 4)) || (d.r2 && d.r2_is_f32 && ((d.r2_ctotal | d.r2_c0) % 4)))

@@ -390,6 +390,7 @@ int build_plan(Rrdbnet* m, int n, int h, int w, uint8_t* wsp, int training, cuda
           d.chunk_c0[ch] = lc < nf ? lc : lc - nf;
         }
         if (k == 0) d.src[1] = nullptr;
+        d.k_valid = nf + k * gc;  // conv2 / conv4: the tail of the last 64-channel chunk has zero weights
         if (k < 4) {
           d.act = 1;
           d.out_bf16 = G; d.ob_ctotal = 4 * gc; d.ob_c0 = k * gc;

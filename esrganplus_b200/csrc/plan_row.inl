@@ -54,6 +54,11 @@ static int plan_row_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
   copy_common(d, &p);
   static const bool no_quad = getenv("ESRP_NO_QUAD") != nullptr;
   p.no_quad = no_quad ? 1 : 0;
+  static const int row_alt = [] { const char* e = getenv("ESRP_ROW_ALT"); return e ? atoi(e) : 1; }();
+  p.row_alt = row_alt;
+  static const bool no_half = getenv("ESRP_NO_HALF_CHUNK") != nullptr;
+  // K-slices of the last chunk beyond k_valid hold zero weights: do not issue them
+  p.last_half = (row_alt && !no_half && d.k_valid > 0 && d.k_valid <= d.num_chunks * KC - KC / 2 && KC >= 32) ? 1 : 0;
   if (make_nhwc_tmap(&out->tm0, d.src[0], d.n, d.h, d.w, d.src_ctotal[0], KC, kRowTile + 2, 1)) return 1;
   if (d.src[1]) {
     if (make_nhwc_tmap(&out->tm1, d.src[1], d.n, d.h, d.w, d.src_ctotal[1], KC, kRowTile + 2, 1)) return 1;

@@ -126,6 +126,11 @@ typedef struct esrp_conv3x3 {
    * instruction.  Private to a caller that owns both producer and consumer of the tensor (the
    * engine's fp32 residual trunk); channel counts / offsets must be multiples of 4. */
   int32_t f32_planar;
+  /* ---- K padding (optional) ----
+   * k_valid > 0: only the first k_valid of the num_chunks*kc input channels carry non-zero weights
+   * (a dense-block conv whose Cin is not a multiple of kc, block.py:253-257: conv2 96, conv4 160).
+   * The kernel may skip MMAs over the zero-weight tail; results are unchanged. */
+  int32_t k_valid;
 } esrp_conv3x3_t;
 
 const char* esrp_last_error(void);

@@ -248,6 +248,38 @@ def test_conv3x3_coscheduled_slices(cuda_dev, shape, train_ext):
         assert (ob1.float() - v).abs().max().item() <= 1e-2 * scale
 
 
+@pytest.mark.parametrize("cin", [96, 160])
+def test_conv3x3_k_valid_skips_zero_weight_tail(cuda_dev, cin):
+    """conv2 / conv4 of a dense block (Cin 96 / 160, block.py:254,256) in 64-channel chunks: the tail of the last chunk
+    has zero weights; with k_valid the kernel does not issue those MMAs.  Garbage (even NaN) in the skipped channels of
+    the source must not reach the output, and the result equals the padded launch bit for bit."""
+    n, h, w = 2, 21, 140
+    g = torch.Generator(device=cuda_dev).manual_seed(cin)
+    nch = (cin + 63) // 64
+    t_in = torch.randn(n, h, w, 64, device=cuda_dev, generator=g).to(torch.bfloat16)
+    gro = torch.randn(n, h, w, 128, device=cuda_dev, generator=g).to(torch.bfloat16)
+    chunks = [(0, 0), (1, 0), (1, 64)][:nch]
+    wt = torch.randn(32, cin, 3, 3, device=cuda_dev, generator=g) / (cin * 9) ** 0.5
+    bias = torch.randn(32, device=cuda_dev, generator=g)
+    wp = K.pack_conv3x3_weights(wt, 64, 32, [64 * i for i in range(nch)], layout=_lib.LAYOUT_ROW)
+    outs = []
+    for kv in (0, cin):
+        out = torch.zeros((n, h, w, 32), device=cuda_dev)
+        K.ConvCall(n=n, h=h, w=w, srcs=[t_in, gro], kc=64, chunks=chunks, bn=32, cout=32, w_packed=wp, w_layout=_lib.LAYOUT_ROW,
+                   bias=bias, act=1, out_f32=out, k_valid=kv).launch()
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    x = torch.cat([t_in, gro], dim=3)[..., :cin].float().permute(0, 3, 1, 2).contiguous()
+    ref = F.leaky_relu(F.conv2d(x, wt.to(torch.bfloat16).float(), bias, padding=1), 0.2)
+    assert (outs[1].permute(0, 3, 1, 2) - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
+    gro2 = gro.clone()
+    gro2[..., cin - 64:] = float("nan")   # channels whose weights are zero: never multiplied when k_valid is given
+    out = torch.zeros((n, h, w, 32), device=cuda_dev)
+    K.ConvCall(n=n, h=h, w=w, srcs=[t_in, gro2], kc=64, chunks=chunks, bn=32, cout=32, w_packed=wp, w_layout=_lib.LAYOUT_ROW,
+               bias=bias, act=1, out_f32=out, k_valid=cin).launch()
+    assert torch.equal(out, outs[1])
+
+
 def test_conv3x3_rejects_bad_arguments(cuda_dev):
     s0 = torch.zeros(1, 8, 8, 64, device=cuda_dev, dtype=torch.bfloat16)
     wp = torch.zeros(9 * 32 * 64 * 2, device=cuda_dev, dtype=torch.uint8)  # 3 ky x 96 rows x 64 ch bf16

@@ -9,7 +9,7 @@
 #include "../esrganplus_b200/csrc/esrp_ptx.cuh"
 using namespace esrp;
 
-struct Cfg { int n, sbo, dstride, nslots, chunks, commit_every, stage_bytes, kx_shift, same_stage, issuers; };
+struct Cfg { int n, sbo, dstride, nslots, chunks, commit_every, stage_bytes, kx_shift, same_stage, issuers, interleave; };
 
 __global__ void __launch_bounds__(128, 1) k(Cfg c, int rows, long long* out) {
   extern __shared__ uint8_t smem_raw[];
@@ -40,7 +40,8 @@ __global__ void __launch_bounds__(128, 1) k(Cfg c, int rows, long long* out) {
           const uint32_t a_lo = alo0 + ((c.same_stage ? 0 : s) * c.stage_bytes >> 4);
           const uint32_t b_lo = blo0 + ((ch * 3 * c.n * 128) >> 4);
           const uint32_t bstep = (c.n * 128) >> 4, astep = c.kx_shift >> 4;
-          const uint32_t d = tmem + slot * c.dstride;
+          // interleave: rows alternate between two independent rings (columns 0.. and 256..) of sliding windows
+          const uint32_t d = c.interleave ? tmem + (r & 1) * 256 + ((r >> 1) % c.nslots) * c.dstride : tmem + slot * c.dstride;
           ++cnt;
           if (elect_one()) {
 #pragma unroll
@@ -94,5 +95,14 @@ int main() {
   run("1 issuer, 3 chunks commit/row",    {96, 1024, 96, 5, 3, 3, 17408, 128, 0, 1});
   run("2 issuers n128 commit/row",{128, 1024, 128, 4, 1, 1, 17408, 128, 0, 2});
   run("2 issuers n32 commit/row", {32, 1024, 96, 5, 1, 1, 17408, 128, 0, 2});
+  // output-stationary ring of conv3x3_row.cuh: consecutive rows accumulate into windows that overlap by 2 of 3 blocks
+  run("1 issuer, sliding D (stride 32)",  {96, 1024, 32, 14, 1, 1, 17408, 128, 0, 1});
+  run("2 issuers, sliding D (stride 32)", {96, 1024, 32, 14, 1, 1, 17408, 128, 0, 2});
+  run("2 issuers, sliding D, 2 chunks",   {96, 1024, 32, 14, 2, 2, 17408, 128, 0, 2});
+  run("2 issuers, sliding D, no commit",  {96, 1024, 32, 14, 1, 0, 17408, 128, 0, 2});
+  run("2 issuers, sliding D, two interleaved rings", {96, 1024, 32, 6, 1, 1, 17408, 128, 0, 2, 1});
+  run("2 issuers, sliding D, two interleaved rings, 2 chunks", {96, 1024, 32, 6, 2, 2, 17408, 128, 0, 2, 1});
+  run("1 issuer, sliding D, two interleaved rings", {96, 1024, 32, 6, 1, 1, 17408, 128, 0, 1, 1});
+  run("2 issuers, disjoint D stride 96, 2 chunks", {96, 1024, 96, 5, 2, 2, 17408, 128, 0, 2});
   return 0;
 }
