@@ -169,7 +169,8 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     tma_prefetch_desc(&tm1);
     for (int i = 0; i < D; ++i) mbar_init(&full_bar[i], 1);
     for (int i = 0; i < kMaxBlocks; ++i) {
-      mbar_init(&blk_full[i], kRowMmaWarps);
+      // row-alternating issue (row_alt == 2): + one plain arrival of the warp that does NOT issue the completing row
+      mbar_init(&blk_full[i], p.row_alt == 2 ? kRowMmaWarps + 1 : kRowMmaWarps);
       mbar_init(&blk_empty[i], 4);
     }
     mbar_init(wfull, 1);
@@ -191,9 +192,9 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
   // every block starts zeroed: all MMAs accumulate
-  if (warp < 4) {
-    const uint32_t la = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    for (int c = 0; c < NBLK * BN; c += 16) tmem_st_zero_x16(la + c);
+  if (warp < kRowEpiWarps) {  // lane quarter warp % 4, a third of the columns each
+    const uint32_t la = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    for (int c = (warp >> 2) * 16; c < NBLK * BN; c += 16 * kRowWGs) tmem_st_zero_x16(la + c);
     tmem_st_wait();
   }
   tcgen05_fence_before();
@@ -343,6 +344,18 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
             }
             __syncwarp();
             tph ^= 1;
+          } else if (p.row_alt == 2) {
+            // The idle warp has now observed every barrier of row I as well.  Its arrival keeps the block (and, through
+            // the producer's wait on it, the row buffer) from being recycled before that: without it a warp that fell
+            // a full ring behind could miss a phase of full_bar / blk_empty and wait for ever.
+            if (lane == 0) {
+              mbar_arrive(&blk_full[pos(O0 + k)]);
+              if (k == ni - 1) {
+                mbar_arrive(&blk_full[pos(O0 + k + 1)]);
+                mbar_arrive(&blk_full[pos(O0 + k + 2)]);
+              }
+            }
+            __syncwarp();
           }
           ++I;
           a_lo += row_step;

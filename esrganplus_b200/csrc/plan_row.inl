@@ -54,7 +54,7 @@ static int plan_row_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
   copy_common(d, &p);
   static const bool no_quad = getenv("ESRP_NO_QUAD") != nullptr;
   p.no_quad = no_quad ? 1 : 0;
-  static const int row_alt = [] { const char* e = getenv("ESRP_ROW_ALT"); return e ? atoi(e) : 1; }();
+  static const int row_alt = [] { const char* e = getenv("ESRP_ROW_ALT"); return e ? atoi(e) : 2; }();
   p.row_alt = row_alt;
   static const bool no_half = getenv("ESRP_NO_HALF_CHUNK") != nullptr;
   // K-slices of the last chunk beyond k_valid hold zero weights: do not issue them

@@ -13,5 +13,5 @@ timeout 900 ncu --metrics $M --clock-control none --profile-from-start off --csv
 timeout 900 ncu --metrics $M --clock-control none --profile-from-start off --csv \
    --log-file gpurun_out/launches_rdb_train.csv python tools/profile_step.py --nb 1 --bwd --train > gpurun_out/ncu_list_rdb.log 2>&1; echo "ncu list rdb rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
-   -k regex:conv3x3_row -s 6 -c 7 -f -o gpurun_out/prof python tools/profile_step.py > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
+   -k regex:conv3x3_row -s 6 -c 6 -f -o gpurun_out/prof python tools/profile_step.py > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
 ncu -i gpurun_out/prof.ncu-rep --page raw --csv > gpurun_out/prof_raw.csv 2>/dev/null; echo "raw rc=$?"
