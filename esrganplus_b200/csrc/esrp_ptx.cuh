@@ -74,13 +74,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Spin on try_wait (which itself suspends in hardware for a bounded time).  A clock-based
-// watchdog (~2 s) turns a protocol bug into a trap (kernel error) instead of a hung GPU box.
+// watchdog (~20 s of SM clocks) turns a protocol bug into a trap (kernel error) instead of a hung GPU box.  It is long
+// on purpose: clock64 keeps counting while a context is switched out or the driver stalls the GPU (an NVML query,
+// another process), and a healthy wait must not trip it.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3FF) == 0 && (clock64() - t0) > 4000000000LL) {
+    if ((++spins & 0x3FF) == 0 && (clock64() - t0) > 40000000000LL) {
       asm volatile("trap;\n");
     }
   }

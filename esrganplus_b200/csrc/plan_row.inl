@@ -55,7 +55,7 @@ static int plan_row_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
   static const bool no_quad = getenv("ESRP_NO_QUAD") != nullptr;
   p.no_quad = no_quad ? 1 : 0;
   static const int row_alt = [] { const char* e = getenv("ESRP_ROW_ALT"); return e ? atoi(e) : 2; }();
-  p.row_alt = row_alt;
+  p.row_alt = row_alt ? 2 : 0;  // 2: alternate rows, the idle issuer adds the third arrival on the block barrier
   static const bool no_half = getenv("ESRP_NO_HALF_CHUNK") != nullptr;
   // K-slices of the last chunk beyond k_valid hold zero weights: do not issue them
   p.last_half = (row_alt && !no_half && d.k_valid > 0 && d.k_valid <= d.num_chunks * KC - KC / 2 && KC >= 32) ? 1 : 0;
