@@ -23,13 +23,23 @@
 //             quarter == warp % 4); 12 TMA producer (ring of row buffers, weights resident); 13-14 MMA
 //             issuers.  tcgen05.mma issue is nearly synchronous (the pipe queues ~1-2 instructions), so
 //             a single issuer leaves a bubble at every barrier wait / commit (85-99 vs 57-61 cycles per
-//             N = 96 MMA, tools/ubench_row.cu).  The two issuers split the TAPS of every row (not the
-//             rows): tcgen05.commit only tracks the MMAs of the committing thread, and with this split
-//             "block complete" == "both warps committed" (mbarrier count 2), independent of any
-//             ordering between the warps.
-//   Barriers: every barrier has in-order waiters that cannot be lapped: a row buffer / block is only
-//             recycled after both issuers committed (producer) resp. after the owning warpgroup
-//             released it (issuers).
+//             N = 96 MMA, tools/ubench_row.cu).  The two issuers ALTERNATE whole input rows (row_alt, the
+//             default): warp (I & 1) issues every tap of row I and passes a turn token; tcgen05.commit
+//             only tracks the MMAs of the committing thread, so a block barrier collects the commit of
+//             the issuer of its last row r+1 (which also issued r-1), the commit of the issuer of its
+//             middle row r, and a plain arrival of the warp that idles during r+1 (count 3).  row_alt = 0
+//             is the earlier protocol: both warps split the taps of every row and both commit (count 2).
+//   Barriers: every barrier has in-order waiters that cannot be lapped, however long a waiter is delayed:
+//             a row buffer / block is only recycled after BOTH issuers have observed every barrier of the
+//             row that completes it (their commits resp. the idle warp's arrival; the producer waits on
+//             that block barrier) and after the owning warpgroup released it (issuers).
+//   Epilogue memory traffic: thread == pixel makes a plain NHWC access one LSU wavefront per lane.  fp32
+//             operands may therefore be [n][h][c/4][w][4] (f32_planar: consecutive lanes touch consecutive
+//             16 bytes), and bf16 outputs go through a 4x4 transpose inside each group of four lanes so
+//             that one store instruction writes 8 x 64 contiguous bytes.
+//   Slices  : a launch may co-schedule nsl slices of BN output channels (nsl = 2: conv5): CTAs
+//             nsl*i .. nsl*i+nsl-1 walk the same rows with the weights / bias / channel offsets of their
+//             slice, so the rows are fetched from DRAM once and every CTA owns nsl times more rows.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
