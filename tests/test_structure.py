@@ -159,3 +159,41 @@ def test_conv_desc_struct_matches_header_size():
     # field-by-field mirror of esrp_conv3x3_t; a size mismatch means the ctypes mirror drifted
     l = _lib.load()
     assert l.esrp_sizeof_conv3x3() == ctypes.sizeof(_lib.Conv3x3Desc)
+
+
+def test_conv_descriptor_validation_of_optional_fields():
+    """Argument checks of esrp_conv3x3_nhwc happen before anything touches a device (error behaviour of the C ABI:
+    non-zero return + esrp_last_error()).  Covers the optional fields: slices / slice_stride, f32_planar, k_valid."""
+    l = _lib.load()
+
+    def desc(**kw):
+        d = _lib.Conv3x3Desc()
+        d.n, d.h, d.w = 1, 8, 200
+        d.src[0] = 0x1000
+        d.src_ctotal[0] = 64
+        d.kc, d.num_chunks, d.bn, d.cout = 64, 1, 32, 32
+        d.chunk_src[0], d.chunk_c0[0] = 0, 0
+        d.w_packed = 0x2000
+        d.w_layout = _lib.LAYOUT_ROW
+        d.s0 = d.s1 = d.s2 = 1.0
+        for k, v in kw.items():
+            setattr(d, k, v)
+        return d
+
+    def err(d):
+        rc = l.esrp_conv3x3_nhwc(ctypes.byref(d), None)
+        assert rc != 0
+        return l.esrp_last_error().decode()
+
+    assert "ESRP_LAYOUT_ROW" in err(desc(slices=2, slice_stride=1024, w_layout=_lib.LAYOUT_TILE))
+    assert "slice_stride" in err(desc(slices=2, slice_stride=0))
+    assert "slice_stride" in err(desc(slices=2, slice_stride=1000))
+    assert "cout == bn" in err(desc(slices=2, slice_stride=1024, cout=16))
+    assert "cout == bn" in err(desc(slices=5, slice_stride=1024))
+    assert "out_nchw" in err(desc(slices=2, slice_stride=1024, out_nchw=0x3000))
+    assert "f32_planar" in err(desc(f32_planar=1, w_layout=_lib.LAYOUT_TILE))
+    assert "f32_planar" in err(desc(f32_planar=1, mask_out=0x3000, mask_out_ctotal=32))
+    assert "k_valid" in err(desc(k_valid=65))
+    assert "k_valid" in err(desc(k_valid=-1))
+    assert "k_valid" in err(desc(num_chunks=2, k_valid=64, src_ctotal=(ctypes.c_int32 * 2)(128, 0),
+                                 chunk_c0=(ctypes.c_int32 * _lib.ESRP_MAX_CHUNKS)(0, 64)))
