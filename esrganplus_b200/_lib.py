@@ -14,6 +14,9 @@ LAYOUT_TILE = 0   # kx-stacked RM x CW tiles (conv3x3_tc.cuh): any width, narrow
 LAYOUT_ROW = 1    # ky-stacked row streaming (conv3x3_row.cuh): images wider than ~64 px, bn <= 32
 
 
+VARIANT_ROW_ALT = 0x2000   # ESRP_VARIANT_ROW_ALT: row kernel, MMA issuers alternate whole rows (include/esrp.h)
+
+
 def variant_mt(mt: int) -> int:
     """esrp_conv3x3_t.variant bits forcing `mt` accumulator slots per CTA tile (ESRP_VARIANT_MT)."""
     return mt & 15

@@ -23,12 +23,13 @@
 //             quarter == warp % 4); 12 TMA producer (ring of row buffers, weights resident); 13-14 MMA
 //             issuers.  tcgen05.mma issue is nearly synchronous (the pipe queues ~1-2 instructions), so
 //             a single issuer leaves a bubble at every barrier wait / commit (85-99 vs 57-61 cycles per
-//             N = 96 MMA, tools/ubench_row.cu).  The two issuers ALTERNATE whole input rows (row_alt, the
-//             default): warp (I & 1) issues every tap of row I and passes a turn token; tcgen05.commit
+//             N = 96 MMA, tools/ubench_row.cu).  With row_alt (ESRP_VARIANT_ROW_ALT, set by
+//             the engine's inference plans) the two issuers ALTERNATE whole input rows: warp (I & 1) issues every tap of row I and passes a turn token; tcgen05.commit
 //             only tracks the MMAs of the committing thread, so a block barrier collects the commit of
 //             the issuer of its last row r+1 (which also issued r-1), the commit of the issuer of its
 //             middle row r, and a plain arrival of the warp that idles during r+1 (count 3).  row_alt = 0
-//             is the earlier protocol: both warps split the taps of every row and both commit (count 2).
+//             (default) is the earlier protocol: both warps split the taps of every row and both commit
+//             (count 2).
 //   Barriers: every barrier has in-order waiters that cannot be lapped, however long a waiter is delayed:
 //             a row buffer / block is only recycled after BOTH issuers have observed every barrier of the
 //             row that completes it (their commits resp. the idle warp's arrival; the producer waits on

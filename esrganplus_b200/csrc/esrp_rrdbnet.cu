@@ -303,9 +303,11 @@ int build_plan(Rrdbnet* m, int n, int h, int w, uint8_t* wsp, int training, cuda
   m->steps.clear();
   const Workspace ws = layout(m, n, h, w);
   const int nf = m->nf, gc = m->gc;
-  auto push_conv = [&](const esrp_conv3x3_t& d, bool patch_y = false, bool is_noise = false, int noise_index = 0) -> int {
+  auto push_conv = [&](const esrp_conv3x3_t& d0, bool patch_y = false, bool is_noise = false, int noise_index = 0) -> int {
     Step st;
     st.kind = Step::kConv;
+    esrp_conv3x3_t d = d0;
+    d.variant |= ESRP_VARIANT_ROW_ALT;  // inference plans: row-alternating MMA issuers where the row kernel runs
     if (plan_conv(d, &st.conv)) return 1;
     st.patch_y = patch_y;
     st.is_noise = is_noise;

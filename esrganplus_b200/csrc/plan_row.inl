@@ -54,7 +54,8 @@ static int plan_row_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
   copy_common(d, &p);
   static const bool no_quad = getenv("ESRP_NO_QUAD") != nullptr;
   p.no_quad = no_quad ? 1 : 0;
-  static const int row_alt = [] { const char* e = getenv("ESRP_ROW_ALT"); return e ? atoi(e) : 2; }();
+  static const int row_alt_env = [] { const char* e = getenv("ESRP_ROW_ALT"); return e ? atoi(e) : -1; }();
+  const bool row_alt = row_alt_env >= 0 ? row_alt_env != 0 : (d.variant & ESRP_VARIANT_ROW_ALT) != 0;
   p.row_alt = row_alt ? 2 : 0;  // 2: alternate rows, the idle issuer adds the third arrival on the block barrier
   static const bool no_half = getenv("ESRP_NO_HALF_CHUNK") != nullptr;
   // K-slices of the last chunk beyond k_valid hold zero weights: do not issue them

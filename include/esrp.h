@@ -32,6 +32,11 @@ extern "C" {
  * pixels (4..7).  Used by tests to exercise every tiling on small inputs. */
 #define ESRP_VARIANT_MT(mt) ((mt) & 15)
 #define ESRP_VARIANT_CWLOG2(l) (((l) & 15) << 4)
+/* Row kernel (ESRP_LAYOUT_ROW): the two MMA-issuer warps alternate whole input rows instead of splitting the taps
+ * of every row (7 % faster on the benchmark forward; also lets k_valid skip zero-weight K-slices).  Opt-in per
+ * launch: the engine sets it for its inference plans, where it has been stress-tested.
+ * The environment variable ESRP_ROW_ALT=0 / 2 overrides every launch (off / on). */
+#define ESRP_VARIANT_ROW_ALT 0x2000
 /* Timing experiments (row kernel; the conv result is WRONG with any of these set). */
 #define ESRP_DBG_NO_XHALO 0x100 /* load boxes at x0 instead of x0-1 (no out-of-bounds on the left)  */
 #define ESRP_DBG_NO_MMA 0x200   /* TMA only: stages are released without issuing MMAs              */

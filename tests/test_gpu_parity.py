@@ -170,7 +170,8 @@ def test_conv3x3_output_channel_slices_and_transposed_pack(cuda_dev, layout):
 
 @pytest.mark.parametrize("shape", [(2, 20, 200), (3, 37, 130), (1, 1, 128), (16, 128, 128)])
 @pytest.mark.parametrize("train_ext", [False, True])
-def test_conv3x3_coscheduled_slices(cuda_dev, shape, train_ext):
+@pytest.mark.parametrize("issuers", [0, _lib.VARIANT_ROW_ALT])   # both MMA-issuer protocols of the row kernel
+def test_conv3x3_coscheduled_slices(cuda_dev, shape, train_ext, issuers):
     """conv5 of a dense block (block.py:258,268; RRDB skip block.py:291) as ONE launch over two 32-channel output
     slices (esrp_conv3x3_t::slices): same arithmetic as two launches, so the results must be bit-identical to them,
     and within the single-conv tolerance of torch conv2d."""
@@ -202,7 +203,7 @@ def test_conv3x3_coscheduled_slices(cuda_dev, shape, train_ext):
         pre = torch.zeros((n, h, w, 64), device=cuda_dev) if train_ext else None
         common = dict(n=n, h=h, w=w, srcs=[t_in, gro], kc=64, chunks=chunks, bn=32, cout=32, w_layout=_lib.LAYOUT_ROW,
                       s0=0.2, r1=r1, s1=1.0, r2=r2, s2=0.2, out_bf16=ob, out_f32=of, noise=1, noise_ctotal=64, seed=77,
-                      offset=5 << 36, pre_f32=pre)
+                      offset=5 << 36, pre_f32=pre, variant=issuers)
         if sliced:
             K.ConvCall(w_packed=buf[:nbytes], bias=biases[0], slices=2, slice_stride=stride, **common).launch()
         else:
@@ -227,7 +228,7 @@ def test_conv3x3_coscheduled_slices(cuda_dev, shape, train_ext):
         K.ConvCall(n=n, h=h, w=w, srcs=[t_in, gro], kc=64, chunks=chunks, bn=32, cout=32, w_layout=_lib.LAYOUT_ROW, s0=0.2,
                    r1=to_planar(r1), s1=1.0, r2=to_planar(r2), s2=0.2, out_bf16=ob3, out_f32=of3, noise=1, noise_ctotal=64,
                    seed=77, offset=5 << 36, w_packed=buf[:nbytes], bias=biases[0], slices=2, slice_stride=stride,
-                   f32_planar=1).launch()
+                   f32_planar=1, variant=issuers).launch()
         assert torch.equal(ob3, ob1) and torch.equal(from_planar(of3), of1)
     if train_ext:
         assert torch.equal(pre1, pre2)
@@ -251,7 +252,7 @@ def test_conv3x3_coscheduled_slices(cuda_dev, shape, train_ext):
 @pytest.mark.parametrize("cin", [96, 160])
 def test_conv3x3_k_valid_skips_zero_weight_tail(cuda_dev, cin):
     """conv2 / conv4 of a dense block (Cin 96 / 160, block.py:254,256) in 64-channel chunks: the tail of the last chunk
-    has zero weights; with k_valid the kernel does not issue those MMAs.  Garbage (even NaN) in the skipped channels of
+    has zero weights; with k_valid (and the row-alternating issuers, ESRP_VARIANT_ROW_ALT) the kernel does not issue those MMAs.  Garbage (even NaN) in the skipped channels of
     the source must not reach the output, and the result equals the padded launch bit for bit."""
     n, h, w = 2, 21, 140
     g = torch.Generator(device=cuda_dev).manual_seed(cin)
@@ -266,7 +267,7 @@ def test_conv3x3_k_valid_skips_zero_weight_tail(cuda_dev, cin):
     for kv in (0, cin):
         out = torch.zeros((n, h, w, 32), device=cuda_dev)
         K.ConvCall(n=n, h=h, w=w, srcs=[t_in, gro], kc=64, chunks=chunks, bn=32, cout=32, w_packed=wp, w_layout=_lib.LAYOUT_ROW,
-                   bias=bias, act=1, out_f32=out, k_valid=kv).launch()
+                   bias=bias, act=1, out_f32=out, k_valid=kv, variant=_lib.VARIANT_ROW_ALT).launch()
         outs.append(out)
     assert torch.equal(outs[0], outs[1])
     x = torch.cat([t_in, gro], dim=3)[..., :cin].float().permute(0, 3, 1, 2).contiguous()
@@ -276,7 +277,7 @@ def test_conv3x3_k_valid_skips_zero_weight_tail(cuda_dev, cin):
     gro2[..., cin - 64:] = float("nan")   # channels whose weights are zero: never multiplied when k_valid is given
     out = torch.zeros((n, h, w, 32), device=cuda_dev)
     K.ConvCall(n=n, h=h, w=w, srcs=[t_in, gro2], kc=64, chunks=chunks, bn=32, cout=32, w_packed=wp, w_layout=_lib.LAYOUT_ROW,
-               bias=bias, act=1, out_f32=out, k_valid=cin).launch()
+               bias=bias, act=1, out_f32=out, k_valid=cin, variant=_lib.VARIANT_ROW_ALT).launch()
     assert torch.equal(out, outs[1])
 
 

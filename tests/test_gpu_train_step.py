@@ -25,7 +25,7 @@ pytestmark = pytest.mark.gpu
 NORM_TOL = {"g": 0.4, "d": 0.25}
 # Bias gradients are sums of sign-alternating terms over all pixels: the norm of G's last bias (model.10.bias, fed by the
 # chaotic D input gradient described above) lands 35 % or 42 % below the fp32 fixture depending only on the order in which
-# the kernel accumulates the taps of a row in fp32 (two valid summation orders, ESRP_ROW_ALT=0/1; cos 0.963 / 0.968).
+# the kernel accumulates the taps of a row in fp32 (two valid summation orders, ESRP_ROW_ALT=0 / 2; cos 0.963 / 0.968).
 BIAS_NORM_TOL = 0.5
 COS_TOL = {"g": 0.8, "d": 0.8}
 
