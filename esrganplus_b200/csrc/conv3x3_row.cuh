@@ -359,10 +359,13 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
             // The idle warp has now observed every barrier of row I as well.  Its arrival keeps the block (and, through
             // the producer's wait on it, the row buffer) from being recycled before that: without it a warp that fell
             // a full ring behind could miss a phase of full_bar / blk_empty and wait for ever.
-            if (lane == 0) {
+            // The last output row of a segment (a real row at the bottom of an image) has only two contributors: row
+            // k-1, issued by THIS warp, and row k.  No later row of this warp commits on its block, so the arrival is a
+            // commit here: it tracks this thread's MMAs of row k-1 (found by tests/test_row_protocol_model.py).
+            if (elect_one()) {
               mbar_arrive(&blk_full[pos(O0 + k)]);
               if (k == ni - 1) {
-                mbar_arrive(&blk_full[pos(O0 + k + 1)]);
+                umma_commit(&blk_full[pos(O0 + k + 1)]);
                 mbar_arrive(&blk_full[pos(O0 + k + 2)]);
               }
             }

@@ -42,6 +42,9 @@ static int plan_row_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
   const int row_bytes = p.a_stage_bytes * d.num_chunks;
   int nbuf = w_all <= avail ? (avail - w_all) / row_bytes : 0;
   if (nbuf > nblk - 2) nbuf = nblk - 2;  // the producer must not be lapped on a block barrier
+  // ... which also needs the blocks touched by nbuf consecutive rows to stay below the ring size.  Every segment end adds
+  // two blocks; images of a few rows put several segments into that window (tests/test_row_protocol_model.py)
+  if (d.h <= nblk - 3 && nbuf > 2) nbuf = 2;
   if (nbuf > kMaxStages) nbuf = kMaxStages;
   const int force = d.variant & 15;
   if (force && force < nbuf) nbuf = force;
