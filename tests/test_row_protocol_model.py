@@ -244,3 +244,36 @@ def test_first_alternating_protocol_could_miss_a_phase():
             found = True
             break
     assert found
+
+
+def _segments_of_cta(n, h, x_tiles, grid, cta):
+    """Input rows per segment of one CTA, following SegWalk / the producer loop of conv3x3_row.cuh."""
+    units = n * x_tiles * h
+    u, u_end = units * cta // grid, units * (cta + 1) // grid
+    segs = []
+    while u < u_end:
+        col = u // h
+        ya = u - col * h
+        cnt = min(u_end - u, h - ya)
+        yb = ya + cnt
+        segs.append(min(yb, h - 1) - max(ya - 1, 0) + 1)
+        u += cnt
+    return segs
+
+
+def test_protocol_on_random_shapes_with_the_planner_rules():
+    """Random batch / height / column-block counts, the CTA's segments as SegWalk cuts them, the number of row buffers as
+    plan_row.inl bounds it (<= blocks - 2, <= 8, two for images of a few rows): both issuer protocols stay live and safe."""
+    rng = random.Random(2024)
+    for case in range(250):
+        nblk = rng.choice([8, 16])
+        n, h, x_tiles = rng.randrange(1, 600), rng.choice([1, 2, 3, 4, 5, 6, 7, 9, 14, 33, 128]), rng.randrange(1, 3)
+        units = n * x_tiles * h
+        grid = min(units, rng.choice([148, 74]))
+        segs = _segments_of_cta(n, h, x_tiles, grid, rng.randrange(grid))
+        stages = rng.randrange(2, min(8, nblk - 2) + 1)
+        if h <= nblk - 3:
+            stages = 2
+        for mode in (0, 2):
+            m, dead = run(mode, nblk, stages, segs, seed=case)
+            assert dead is None and not m.errors, (mode, nblk, stages, n, h, x_tiles, grid, segs, dead, m.errors[:2])
