@@ -81,16 +81,33 @@ int make_nhwc_tmap(CUtensorMap* tm, const void* ptr, int n, int h, int w, int c_
 // conv launch
 // ------------------------------------------------------------------------------------------------
 
-static int g_sm_count = 0;
+// Per-device state is keyed by the device ordinal: one process may drive several GPUs (nn.DataParallel, gpu_ids=[0,1]).
+static std::mutex g_dev_mu;
 int sm_count() {
-  if (g_sm_count == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return -1;
-    g_sm_count = prop.multiProcessorCount;
+  static int counts[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (counts[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    counts[dev] = n;
   }
-  return g_sm_count;
+  return counts[dev];
+}
+
+int ensure_max_smem(const void* kernel, int bytes) {
+  static std::unordered_map<std::string, int>* done = new std::unordered_map<std::string, int>();
+  int dev = 0;
+  ESRP_CUDA_OK(cudaGetDevice(&dev));
+  char key[64];
+  snprintf(key, sizeof(key), "%d:%p", dev, kernel);
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  auto it = done->find(key);
+  if (it != done->end() && it->second >= bytes) return 0;
+  ESRP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  (*done)[key] = bytes;
+  return 0;
 }
 
 // kernel instantiations live in esrp_conv_{row,tile}{,_ext}.cu (one translation unit per family so they build in parallel)

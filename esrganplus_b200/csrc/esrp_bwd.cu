@@ -521,11 +521,7 @@ int plan_wgrad(const esrp_wgrad_unit_t* units, int num_units, int n, int h, int 
   p.splits = splits;
   out->grid = num_units * splits;
   out->smem = 2 * p.stage_bytes;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ESRP_CUDA_OK(cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 48 * 1024));
-    attr_set = true;
-  }
+  if (ensure_max_smem(reinterpret_cast<const void*>(conv3x3_wgrad_kernel), 2 * 48 * 1024)) return 1;
   if (out->smem > 2 * 48 * 1024) return set_error("wgrad: internal: stage too large");
   return 0;
 }

@@ -170,6 +170,8 @@ void esrp_rrdbnet_destroy(esrp_rrdbnet_t* h) {
   Rrdbnet* m = reinterpret_cast<Rrdbnet*>(h);
   if (!m) return;
   destroy_train_state(m);
+  for (Step& st : m->steps)
+    if (st.kind == Step::kChain) free_chain(&st.chain);
   if (m->pack_jobs_dev) cudaFree(m->pack_jobs_dev);
   if (m->wbuf) cudaFree(m->wbuf);
   delete m;
@@ -299,8 +301,50 @@ Workspace layout(const Rrdbnet* m, int n, int h, int w) {
   return ws;
 }
 
-int build_plan(Rrdbnet* m, int n, int h, int w, uint8_t* wsp, int training, cudaStream_t stream) {
+void clear_steps(Rrdbnet* m) {
+  for (Step& st : m->steps)
+    if (st.kind == Step::kChain) free_chain(&st.chain);
   m->steps.clear();
+}
+
+// Merge every run of >= 2 consecutive chain-compatible conv launches (the dense-block convs of the trunk) into one
+// persistent launch.  ESRP_NO_CHAIN=1 keeps one launch per conv (A/B timing, bisecting).
+int merge_chains(Rrdbnet* m) {
+  static const bool off = getenv("ESRP_NO_CHAIN") != nullptr;
+  if (off || !m->use_chain) return 0;
+  std::vector<Step> out;
+  size_t i = 0;
+  while (i < m->steps.size()) {
+    size_t j = i;
+    auto ok = [&](const Step& s) {
+      return s.kind == Step::kConv && !s.patch_y && !s.is_noise && chain_compatible(s.conv) &&
+             s.conv.grid == m->steps[i].conv.grid;
+    };
+    while (j < m->steps.size() && ok(m->steps[j])) ++j;
+    if (j - i >= 2) {
+      std::vector<const ConvLaunch*> cs;
+      for (size_t k = i; k < j; ++k) cs.push_back(&m->steps[k].conv);
+      Step st;
+      st.kind = Step::kChain;
+      st.chain_convs = static_cast<int>(j - i);
+      if (plan_chain(cs.data(), static_cast<int>(cs.size()), &st.chain)) {
+        for (Step& o : out)
+          if (o.kind == Step::kChain) free_chain(&o.chain);
+        return 1;
+      }
+      out.push_back(st);
+      i = j;
+    } else {
+      out.push_back(m->steps[i]);
+      ++i;
+    }
+  }
+  m->steps.swap(out);
+  return 0;
+}
+
+int build_plan(Rrdbnet* m, int n, int h, int w, uint8_t* wsp, int training, cudaStream_t stream) {
+  clear_steps(m);
   const Workspace ws = layout(m, n, h, w);
   const int nf = m->nf, gc = m->gc;
   auto push_conv = [&](const esrp_conv3x3_t& d0, bool patch_y = false, bool is_noise = false, int noise_index = 0) -> int {
@@ -448,6 +492,7 @@ int build_plan(Rrdbnet* m, int n, int h, int w, uint8_t* wsp, int training, cuda
   // 6. HR_conv1 (architecture.py:71): NCHW fp32 straight into the caller's output tensor
   if (plain(m->hr1, ch_, cw_, hr0_out, nf, 0, nullptr, nullptr, nullptr, true)) return 1;
 
+  if (merge_chains(m)) return 1;
   m->pn = n; m->ph = h; m->pw = w; m->pws = wsp; m->ptraining = training;
   m->g_zeroed = false;
   return 0;
@@ -467,6 +512,25 @@ int64_t esrp_rrdbnet_workspace_bytes(const esrp_rrdbnet_t* h, int32_t n, int32_t
 int32_t esrp_rrdbnet_num_launches(const esrp_rrdbnet_t* h) {
   const Rrdbnet* m = reinterpret_cast<const Rrdbnet*>(h);
   return m ? static_cast<int32_t>(m->steps.size()) : -1;
+}
+
+int esrp_rrdbnet_set_chain(esrp_rrdbnet_t* h, int32_t enable) {
+  Rrdbnet* m = reinterpret_cast<Rrdbnet*>(h);
+  if (!m) return set_error("rrdbnet_set_chain: null handle");
+  if (m->use_chain != (enable != 0)) {
+    m->use_chain = enable != 0;
+    m->pn = 0;  // re-plan at the next forward
+  }
+  return 0;
+}
+
+int32_t esrp_rrdbnet_num_chained_convs(const esrp_rrdbnet_t* h) {
+  const Rrdbnet* m = reinterpret_cast<const Rrdbnet*>(h);
+  if (!m) return -1;
+  int32_t n = 0;
+  for (const Step& st : m->steps)
+    if (st.kind == Step::kChain) n += st.chain_convs;
+  return n;
 }
 
 int esrp_rrdbnet_forward(esrp_rrdbnet_t* h, const float* x, float* y, int32_t n, int32_t hh, int32_t w,
@@ -518,6 +582,9 @@ int esrp_rrdbnet_forward(esrp_rrdbnet_t* h, const float* x, float* y, int32_t n,
         break;
       case Step::kUpsample:
         if (esrp_upsample2x_nhwc_bf16(st.src, st.dst, st.n, st.h, st.w, st.c, stream)) return 1;
+        break;
+      case Step::kChain:
+        if (run_chain(st.chain, s)) return 1;
         break;
       case Step::kConv:
         if (st.patch_y) st.conv.params.out_nchw = y;

@@ -28,8 +28,10 @@ struct ConvW {
 };
 
 struct Step {
-  enum Kind { kConv, kPackInput, kUpsample } kind = kConv;
+  enum Kind { kConv, kPackInput, kUpsample, kChain } kind = kConv;
   ConvLaunch conv;
+  ChainLaunch chain;         // kChain: a run of row-kernel convs merged into one persistent launch (conv3x3_chain.cuh)
+  int chain_convs = 0;       //   how many conv launches it replaced
   const void* src = nullptr;
   void* dst = nullptr;
   int n = 0, h = 0, w = 0, c = 0, c_pad = 0;
@@ -60,6 +62,7 @@ struct Rrdbnet {
   int pn = 0, ph = 0, pw = 0, ptraining = -1;
   void* pws = nullptr;
   bool g_zeroed = false;
+  bool use_chain = true;              // merge runs of row-kernel convs into persistent chain launches (esrp_rrdbnet_set_chain)
   std::vector<Step> steps;
   TrainState* train = nullptr;        // training plan + dgrad weight cache (lazily created)
   const uint8_t* x_u8 = nullptr;     // set for the duration of esrp_rrdbnet_forward_u8: the input is an 8-bit HWC image

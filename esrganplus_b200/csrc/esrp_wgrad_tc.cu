@@ -328,11 +328,7 @@ int plan_wgrad_tc(const esrp_wgrad_unit_t* units, int num_units, int n, int h, i
   out->smem = p.stages * p.stage_bytes + 1024;
   out->tc = 1;
   out->npx = static_cast<long long>(n) * h * w;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ESRP_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 1024));
-    attr_set = true;
-  }
+  if (ensure_max_smem(reinterpret_cast<const void*>(wgrad_tc_kernel), kMaxSmem - 1024)) return 1;
   if (out->smem > kMaxSmem - 1024) return set_error("wgrad(tc): internal: stages do not fit in shared memory");
   return 0;
 }

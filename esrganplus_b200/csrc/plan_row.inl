@@ -70,13 +70,10 @@ static int plan_row_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
     out->tm1 = out->tm0;
   }
   auto kern = conv3x3_row_kernel<KC, BN, AUX, EXT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ESRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    attr_set = true;
-  }
+  if (ensure_max_smem(reinterpret_cast<const void*>(kern))) return 1;
   out->kernel = reinterpret_cast<const void*>(kern);
   out->threads = kRowThreads;
+  out->fam = 1; out->kc = KC; out->bn = BN; out->ext = EXT ? 1 : 0;
   const int sms = sm_count();
   if (sms <= 0) return set_error("conv3x3: no CUDA device");
   // co-scheduled slices: groups of nsl CTAs share a row range

@@ -99,11 +99,7 @@ static int plan_conv_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
   }
 
   auto kern = conv3x3_tc_kernel<KC, BN, EXT>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
-    ESRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    attr_set = true;
-  }
+  if (ensure_max_smem(reinterpret_cast<const void*>(kern))) return 1;
   out->kernel = reinterpret_cast<const void*>(kern);
   out->threads = kConvThreads;
   out->grid = p.units_total < sms ? static_cast<int>(p.units_total) : sms;

@@ -128,6 +128,15 @@ class GeneratorEngine:
     def num_launches(self) -> int:
         return self.lib.esrp_rrdbnet_num_launches(self.handle)
 
+    @property
+    def num_chained_convs(self) -> int:
+        """Conv launches that the persistent chains of the last planned forward replaced."""
+        return self.lib.esrp_rrdbnet_num_chained_convs(self.handle)
+
+    def set_chain(self, enable: bool) -> None:
+        """One persistent launch for the dense-block convs of the trunk (default) or one launch per conv."""
+        _lib.check(self.lib.esrp_rrdbnet_set_chain(self.handle, int(bool(enable))), "esrp_rrdbnet_set_chain")
+
     # -- training --------------------------------------------------------------------------------
     def _check_input(self, x: torch.Tensor) -> torch.Tensor:
         if x.dim() != 4 or x.dtype != torch.float32 or x.device != self.device:

@@ -324,6 +324,13 @@ int esrp_rrdbnet_load_weights(esrp_rrdbnet_t* h, const void* const* ptrs, int32_
 int64_t esrp_rrdbnet_workspace_bytes(const esrp_rrdbnet_t* h, int32_t n, int32_t hgt, int32_t w);
 /* Kernel launches in the most recently planned forward (for bench.py's gpu_launches). */
 int32_t esrp_rrdbnet_num_launches(const esrp_rrdbnet_t* h);
+/* Persistent conv chain (default on): consecutive row-kernel convs of the inference plan — the five convs of every
+ * ResidualDenseBlock_5C of the trunk (block.py:260-268) — run as phases of ONE launch that synchronises row
+ * neighbours through flags in device memory (csrc/conv3x3_chain.cuh) instead of one launch per conv.  enable = 0
+ * restores one launch per conv (A/B measurements, tests).  The next forward re-plans. */
+int esrp_rrdbnet_set_chain(esrp_rrdbnet_t* h, int32_t enable);
+/* Conv launches the chains of the most recently planned forward replaced (0 when none was built). */
+int32_t esrp_rrdbnet_num_chained_convs(const esrp_rrdbnet_t* h);
 /* x: NCHW fp32 [n,in_nc,h,w] -> y: NCHW fp32 [n,out_nc,upscale*h,upscale*w] (unclamped, like the
  * reference).  training!=0 enables the per-RDB multiplicative Gaussian noise (block.py:117-121)
  * drawn from Philox(seed).  workspace: 1024-byte aligned device memory of at least

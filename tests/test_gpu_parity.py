@@ -452,6 +452,56 @@ def test_config2_full_size_properties(cuda_dev):
     _net_close(y1.cpu(), ref, "config 2 tile 3")
 
 
+# ---------------------------------------------------------------------------------------------------
+# persistent conv chain (csrc/conv3x3_chain.cuh): the dense-block convs of the trunk as phases of ONE launch
+# ---------------------------------------------------------------------------------------------------
+# ragged widths, several images per CTA range, CTA ranges that cross image boundaries, images wider than one
+# 128-pixel tile (dep_all), fewer rows than SMs (conv5 keeps its own launch: another grid), one-row images
+CHAIN_SHAPES = [(3, 37, 100), (2, 70, 128), (1, 9, 300), (5, 3, 130), (4, 64, 65), (2, 1, 128), (7, 128, 128)]
+
+
+@pytest.mark.parametrize("shape", CHAIN_SHAPES)
+def test_chain_matches_per_conv_launches_and_oracle(cuda_dev, shape):
+    n, h, w = shape
+    nb = 2
+    sd = O.synth_state_dict_g(3, 3, 64, nb, seed=41)
+    net = _make(E.RRDBNet, sd, 64, nb, cuda_dev)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(n, 3, h, w, generator=g)
+    xd = x.to(cuda_dev)
+    eng = net._engine_for(cuda_dev)
+    y = net(xd)
+    assert eng.num_chained_convs >= 4 * 3 * nb, (eng.num_chained_convs, eng.num_launches)
+    # the two issuer threads hand whole rows over in order: the accumulation order is fixed, results reproduce bit for bit
+    for _ in range(3):
+        assert torch.equal(net(xd), y), "chain results must be run-to-run identical"
+    eng.set_chain(False)
+    y_plain = net(xd)
+    assert eng.num_chained_convs == 0
+    eng.set_chain(True)
+    assert torch.equal(net(xd), y)
+    d = (y - y_plain).abs().max().item() / y_plain.std().item()
+    assert d <= NET_REL_TOL / 10, f"chain vs one launch per conv: {d:.3e}"
+    if n * h * w <= 3 * 37 * 130:
+        _net_close(y.cpu(), O.rrdbnet_forward(x, sd, nb), f"chain {shape}")
+
+
+def test_chain_nb23_many_phases_back_to_back(cuda_dev):
+    """345 phases per launch, 12 launches back to back (flags are reset per launch), 6 images of 96 rows so that CTA
+    ranges cross image boundaries: every result identical, and one tile checked against the fp32 oracle."""
+    sd = O.synth_state_dict_g(3, 3, 64, 23, seed=31)
+    net = _make(E.RRDBNet, sd, 64, 23, cuda_dev)
+    g = torch.Generator().manual_seed(6)
+    x = torch.rand(6, 3, 96, 128, generator=g)
+    xd = x.to(cuda_dev)
+    eng = net._engine_for(cuda_dev)
+    y = net(xd)
+    assert eng.num_chained_convs == 345 and eng.num_launches <= 12, (eng.num_chained_convs, eng.num_launches)
+    for _ in range(11):
+        assert torch.equal(net(xd), y)
+    _net_close(net(xd[2:3]).cpu(), O.rrdbnet_forward(x[2:3], sd, 23), "chain nb23 tile 2")
+
+
 def test_tiled_inference_matches_oracle_per_crop(cuda_dev):
     """BASELINE config 3 in miniature: an LR image cut into independent crops (esrganplus_b200/tiled.py);
     parity is per crop (zero padding at crop edges), exactly like running the reference on each crop."""
