@@ -29,7 +29,38 @@ def _flat(*groups) -> nn.Sequential:
     return nn.Sequential(*mods)
 
 
-class _GeneratorBase(nn.Module):
+class _NativeWeights:
+    """Mixin of the top-level classes: the native engines keep DERIVED bf16 weight tiles and repack them when a
+    Parameter's storage pointer or in-place version counter changes.  Writes through ``.data`` bump no version
+    counter (``m.weight.data *= scale`` / ``init.kaiming_normal_(m.weight.data)`` in the reference's ``init_weights``,
+    networks.py:30-44, run via ``net.apply(fn)``), so every bulk entry point that may hide such writes bumps an
+    epoch the engines compare as well: ``apply``, ``_apply`` (``.to()`` / ``.cuda()``), ``load_state_dict``.  After any
+    other ``.data`` write (EMA, weight interpolation, clipping) call ``invalidate_weights()``."""
+
+    def invalidate_weights(self) -> None:
+        object.__setattr__(self, "_esrp_epoch", self.__dict__.get("_esrp_epoch", 0) + 1)
+
+    @property
+    def weights_epoch(self) -> int:
+        return self.__dict__.get("_esrp_epoch", 0)
+
+    def apply(self, fn):
+        r = super().apply(fn)
+        self.invalidate_weights()
+        return r
+
+    def _apply(self, fn, *args, **kwargs):
+        r = super()._apply(fn, *args, **kwargs)
+        self.invalidate_weights()
+        return r
+
+    def load_state_dict(self, *args, **kwargs):
+        r = super().load_state_dict(*args, **kwargs)
+        self.invalidate_weights()
+        return r
+
+
+class _GeneratorBase(_NativeWeights, nn.Module):
     def _build(self, in_nc, out_nc, nf, nb, gc, upscale, norm_type, act_type, mode, upsample_mode, rrdb_noise):
         if upsample_mode not in ("upconv", "pixelshuffle"):
             raise NotImplementedError("upsample mode [{:s}] is not found".format(upsample_mode))
@@ -89,7 +120,7 @@ class _GeneratorBase(nn.Module):
         from .discriminator import _named_params
         names, plist = _named_params(self)
         eng = self._engine_for(img.device)
-        eng.sync_weights(dict(zip(names, plist)))
+        eng.sync_weights(dict(zip(names, plist)), self.weights_epoch)
         return eng.forward_u8(img, bgr)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -104,7 +135,7 @@ class _GeneratorBase(nn.Module):
             from .autograd import generator_apply
             return generator_apply(self, x, params)
         eng = self._engine_for(x.device)
-        eng.sync_weights(params)
+        eng.sync_weights(params, self.weights_epoch)
         return eng.forward(x, self.training, self.noise_seed() if self.training else 0)
 
 
@@ -133,7 +164,7 @@ class RRDB_Net(_GeneratorBase):
         return super().forward(x)
 
 
-class Discriminator_VGG_128(nn.Module):
+class Discriminator_VGG_128(_NativeWeights, nn.Module):
     """architecture.py:87-129.  Ten conv layers (k3 s1 / k4 s2 alternating, BatchNorm2d from the second
     on, LeakyReLU 0.2) 128x128 -> 4x4, then Linear(8192,100) + LeakyReLU + Linear(100,1)."""
 

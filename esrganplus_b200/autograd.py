@@ -55,7 +55,7 @@ def generator_apply(module, x: torch.Tensor, params: Dict[str, torch.Tensor]) ->
             "esrganplus_b200.RRDBNet: the gradient w.r.t. the LR input is not produced (the reference never asks "
             "for it, SRRaGAN_model.py:103-111); detach the input")
     eng = module._engine_for(x.device)
-    eng.sync_weights(params)
+    eng.sync_weights(params, module.weights_epoch)
     plist = []
     for k in eng.keys:
         plist.append(params[k])

@@ -39,15 +39,17 @@ int plan_tile_base(const esrp_conv3x3_t& d, ConvLaunch* out);
 int plan_tile_ext(const esrp_conv3x3_t& d, ConvLaunch* out);
 void copy_common(const esrp_conv3x3_t& d, ConvKParams* pp);
 // A persistent chain of row-kernel convs executed by ONE launch (conv3x3_chain.cuh): the phase table (tensor maps +
-// kernel parameters of every conv) and the per-CTA completion flags live in device memory owned by this object.
+// a compact record per conv) is the kernel's parameter block, kept on the host; the per-CTA completion flags live in
+// device memory owned by this object.
 struct ChainLaunch {
   const void* kernel = nullptr;
-  void* dev_phases = nullptr;
+  void* args_host = nullptr;   // ChainArgs (malloc)
   unsigned int* dev_flags = nullptr;
   int num_phases = 0;
   int dep_all = 0;
   int grid = 0, threads = 0, smem = 0;
 };
+constexpr int kChainMaxPhasesHost = 440;  // == kChainMaxPhases (conv3x3_chain.cuh): phases per chain launch
 // true when the launch can be a phase of a chain (row kernel, kc = 64, bn = 32, NHWC outputs only)
 bool chain_compatible(const ConvLaunch& L);
 int plan_chain(const ConvLaunch* const* convs, int count, ChainLaunch* out);

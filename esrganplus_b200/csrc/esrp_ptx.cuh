@@ -119,6 +119,13 @@ __device__ __forceinline__ void tma_load_4d_hint(void* smem_dst, const void* tma
         "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
       : "memory");
 }
+// L2 prefetch of a 4-D tile (no shared-memory destination, no barrier): a later tma_load_4d of the same box hits L2.
+__device__ __forceinline__ void tma_prefetch_4d(const void* tmap, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];\n"
+               :
+               : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ float4 ld_global_f4_hint(const float4* p, uint64_t policy) {
   float4 v;
   asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;\n"

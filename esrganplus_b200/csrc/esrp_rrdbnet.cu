@@ -312,6 +312,7 @@ void clear_steps(Rrdbnet* m) {
 int merge_chains(Rrdbnet* m) {
   static const bool off = getenv("ESRP_NO_CHAIN") != nullptr;
   if (off || !m->use_chain) return 0;
+  static const size_t max_run = [] { const char* e = getenv("ESRP_CHAIN_MAX"); return e ? static_cast<size_t>(atoi(e)) : static_cast<size_t>(kChainMaxPhasesHost); }();
   std::vector<Step> out;
   size_t i = 0;
   while (i < m->steps.size()) {
@@ -320,8 +321,8 @@ int merge_chains(Rrdbnet* m) {
       return s.kind == Step::kConv && !s.patch_y && !s.is_noise && chain_compatible(s.conv) &&
              s.conv.grid == m->steps[i].conv.grid;
     };
-    while (j < m->steps.size() && ok(m->steps[j])) ++j;
-    if (j - i >= 2) {
+    while (j < m->steps.size() && j - i < max_run && ok(m->steps[j])) ++j;
+    if (j - i >= 2 || (j - i == 1 && max_run == 1)) {
       std::vector<const ConvLaunch*> cs;
       for (size_t k = i; k < j; ++k) cs.push_back(&m->steps[k].conv);
       Step st;

@@ -140,6 +140,7 @@ class DiscriminatorEngine:
         self._rec: Optional[list] = None     # call list being recorded
         self._keep: Optional[list] = None    # keep-alive list of the plan being recorded
         self._ptr_sig = None
+        self.epoch = 0
         feats = list(module.features)
         self.layers: List[_Layer] = []
         i = 0
@@ -201,7 +202,7 @@ class DiscriminatorEngine:
         """Derived weight tensors follow the Parameter (pointer / in-place version).  They are rebuilt IN PLACE: recorded
         launch plans keep pointing at the same packed tiles, bias vector and 3x3 view of a 4x4 weight."""
         w, b = L.conv.weight, L.conv.bias
-        sig = (w.data_ptr(), w._version, b.data_ptr() if b is not None else 0, b._version if b is not None else 0)
+        sig = (w.data_ptr(), w._version, b.data_ptr() if b is not None else 0, b._version if b is not None else 0, self.epoch)
         if sig == L.sig:
             return
         if w.device != self.device or w.dtype != torch.float32:
@@ -306,6 +307,7 @@ class DiscriminatorEngine:
         if x.shape[2] != 128 or x.shape[3] != 128:
             raise RuntimeError("Discriminator_VGG_128 expects 128x128 inputs (classifier is Linear(512*4*4, 100))")
         x = x.contiguous()
+        self.epoch = module.__dict__.get("_esrp_epoch", 0)   # bumped by apply / .to() / load_state_dict / invalidate_weights
         for L in self.layers:
             self._sync(L)
         plan = self._acquire(module, n)

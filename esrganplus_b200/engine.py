@@ -42,9 +42,10 @@ class GeneratorEngine:
             pass
 
     # -- weights ---------------------------------------------------------------------------------
-    def sync_weights(self, named_params: Dict[str, torch.Tensor]) -> bool:
+    def sync_weights(self, named_params: Dict[str, torch.Tensor], epoch: int = 0) -> bool:
         """Repack if any source tensor changed. `named_params`: state_dict-style key -> fp32 tensor
-        on this device. Returns True when a repack was launched."""
+        on this device; `epoch`: the module's invalidation counter (writes through ``.data`` bump no tensor
+        version, see architecture._NativeWeights). Returns True when a repack was launched."""
         tensors = []
         for k in self.keys:
             t = named_params.get(k)
@@ -53,7 +54,7 @@ class GeneratorEngine:
             if t.device != self.device or t.dtype != torch.float32:
                 raise RuntimeError(f"RRDBNet engine: {k} must be fp32 on {self.device}, got {t.dtype} on {t.device}")
             tensors.append(t if t.is_contiguous() else t.contiguous())
-        sig = tuple((t.data_ptr(), t._version) for t in tensors)
+        sig = (epoch, tuple((t.data_ptr(), t._version) for t in tensors))
         if sig == self._sig:
             return False
         ptrs = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
