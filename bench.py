@@ -17,6 +17,12 @@ Inference shards independent tiles across ranks with no collective (weak scaling
 `cpu_baseline` / --impl reference: the reference's algorithm (CPU oracle = torch CPU fp32 ops, the
              same ATen kernels the reference's nn.Conv2d dispatches to) on this box's host cores, on
              a bounded sample (one 128x128 tile per step).
+`tiled`      BASELINE.json config 3: ONE 512x512 LR image cut into 16 crops of 128x128, sharded over the ranks
+             (esrganplus_b200.tiled, no collective on the data path): latency per image and MP/s, strong scaling.
+`chain`      the same forward with the opt-in persistent conv chain (10 launches instead of 354; slower).
+`gpu_library_baseline` (N = 1): the oracle's functional forward (torch ops = cuDNN) on the SAME GPU in fp32, TF32 and
+             bf16 autocast + channels_last — a library baseline, never routed through the product.
+A device fault fails the run (there is no retry): the JSON line exists only if every leg of the headline ran clean.
 """
 from __future__ import annotations
 
@@ -86,6 +92,18 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
+def csrc_hash() -> str:
+    """sha256 over the kernel sources: ties a committed ncu capture to the library build it was taken from."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "esrganplus_b200", "csrc")
+    for f in sorted(glob.glob(os.path.join(d, "*.cu")) + glob.glob(os.path.join(d, "*.cuh")) + glob.glob(os.path.join(d, "*.inl")) +
+                    glob.glob(os.path.join(d, "*.h")) + [os.path.join(ROOT, "include", "esrp.h")]):
+        h.update(open(f, "rb").read())
+    return h.hexdigest()
+
+
 def cpu_reference_run(steps: int, warmup: int, threads: int):
     """The reference's CPU path on a bounded sample: one 128x128 tile per step, fp32, all host threads."""
     import torch
@@ -101,6 +119,48 @@ def cpu_reference_run(steps: int, warmup: int, threads: int):
             O.rrdbnet_forward(x, sd, NB)
         dt = (time.perf_counter() - t0) / steps
     return OUT_MP_PER_TILE / dt, dt
+
+
+def gpu_library_baseline(torch, dev, sd, x):
+    """The reference's own operator graph (oracle = functional restatement of block.py / architecture.py) executed by
+    PyTorch's CUDA libraries (cuDNN convs, ATen elementwise, torch.cat) on the same GPU and the same batch: what a user
+    of the unmodified reference gets on a B200.  fp32 with TF32 off (the reference's arithmetic), TF32 on, and bf16
+    autocast with channels_last.  Test infrastructure used as a measured baseline only."""
+    from oracle import esrgan_oracle as O
+    sdd = {k: v.to(dev) for k, v in sd.items()}
+    out = {}
+
+    def run(label, xin, weights, steps=3):
+        with torch.no_grad():
+            for _ in range(2):
+                O.rrdbnet_forward(xin, weights, NB)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                O.rrdbnet_forward(xin, weights, NB)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[label] = {"ms_per_step": ms, "value": BATCH * OUT_MP_PER_TILE / (ms * 1e-3), "unit": "MP/s"}
+
+    old_c, old_m, old_b = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark
+    try:
+        torch.backends.cudnn.benchmark = True
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        run("fp32_cudnn", x, sdd)
+        torch.backends.cudnn.allow_tf32 = True
+        torch.backends.cuda.matmul.allow_tf32 = True
+        run("tf32_cudnn", x, sdd)
+        sd_cl = {k: (v.to(memory_format=torch.channels_last) if v.dim() == 4 else v) for k, v in sdd.items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            run("bf16_autocast_channels_last", x.to(memory_format=torch.channels_last), sd_cl)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old_c, old_m
+        torch.backends.cudnn.benchmark = old_b
+    out["note"] = "oracle.rrdbnet_forward on CUDA (cuDNN / ATen), same batch of 16 tiles, 3 timed steps each"
+    return out
 
 
 def main_reference(args):
@@ -258,11 +318,16 @@ def main_ours(args):
     with torch.no_grad():
         for _ in range(max(3, args.warmup)):
             step_resident()
+        # the dense-block convs of the trunk (the dominant kernel family) are bracketed by a pair of CUDA events per forward,
+        # recorded by the engine on the launching stream inside the timed region below (esrp_rrdbnet_set_timing)
+        net._engines[dev].set_timing(True)
         sampler = ClockSampler(local) if rank == 0 else None
         if sampler:
             sampler.start()
         ms = timed(step_resident, args.steps)
         clocks = sampler.stop() if sampler else None
+        trunk_ms = net._engines[dev].trunk_times_ms(min(args.steps, 64))
+        net._engines[dev].set_timing(False)
         for _ in range(2):
             step_e2e()
         ms_e2e = timed(step_e2e, args.steps, join=copy_stream)
@@ -292,11 +357,55 @@ def main_ours(args):
                   "ms_per_step": ms_u8 / args.steps, "api": "RRDBNet.forward_uint8 (uint8 HWC in/out, plumbing on the device)"}
     except Exception as e:
         e2e_u8 = {"error": f"{type(e).__name__}: {e}"[:300]}
+    # ---- secondary inference legs -------------------------------------------------------------------------------
+    chain_leg = tiled_leg = lib_leg = None
+    eng = net._engines[dev]
+    launches_plain = eng.num_launches
+    if not args.no_extras:
+        try:    # the opt-in persistent conv chain on the same workload
+            eng.set_chain(True)
+            with torch.no_grad():
+                for _ in range(3):
+                    step_resident()
+                ms_c = timed(step_resident, args.steps)
+            chain_leg = {"value": BATCH * OUT_MP_PER_TILE * world / (ms_c / args.steps * 1e-3), "unit": "MP/s",
+                         "ms_per_step": ms_c / args.steps, "launches_per_step": eng.num_launches,
+                         "convs_chained": eng.num_chained_convs,
+                         "note": "esrp_rrdbnet_set_chain(1): dense-block convs as phases of one persistent launch"}
+        except Exception as e:
+            chain_leg = {"error": f"{type(e).__name__}: {e}"[:300]}
+        finally:
+            eng.set_chain(False)
+        try:    # config 3: one 512x512 LR image, 16 crops sharded over the ranks, no collective on the data path
+            from esrganplus_b200 import tiled as T
+            img = torch.rand(1, 3, 4 * TILE, 4 * TILE, generator=torch.Generator().manual_seed(7)).to(dev)
+            crops = T.crop_grid(4 * TILE, 4 * TILE, TILE)
+            mine = T.shard(list(range(len(crops))), rank, world)
+
+            def step_tiled():
+                return T.run_crops(net, img, [crops[i] for i in mine], 4)
+
+            with torch.no_grad():
+                for _ in range(3):
+                    step_tiled()
+                ms_t = timed(step_tiled, args.steps)
+            per_img = ms_t / args.steps
+            tiled_leg = {"metric": "x4_sr_tiled_image_latency_ms", "value": per_img, "unit": "ms per 512x512 LR image",
+                         "mp_per_s": (16 * TILE * TILE * 16 / 1e6) / (per_img * 1e-3), "crops": len(crops),
+                         "crops_per_rank": len(mine), "scaling": "strong", "collective": None,
+                         "workload": "one 512x512 LR image -> 2048x2048, 16 crops of 128x128 sharded round-robin (config 3)"}
+        except Exception as e:
+            tiled_leg = {"error": f"{type(e).__name__}: {e}"[:300]}
+        if world == 1:
+            try:
+                lib_leg = gpu_library_baseline(torch, dev, sd, x_dev)
+            except Exception as e:
+                lib_leg = {"error": f"{type(e).__name__}: {e}"[:300]}
     train = train_strong = None
     if not args.no_train:
         # the inference legs leave ~2.5 GB of cached workspace behind and the GPU at its power cap: hand the memory back and
         # let the clocks settle before the secondary measurement
-        launches_inf = net._engines[dev].num_launches
+        launches_inf = launches_plain
         del y_hosts, x_dev
         net._engines.clear()
         torch.cuda.empty_cache()
@@ -308,7 +417,7 @@ def main_ours(args):
         except Exception as e:  # the headline line must survive a failure of the secondary leg
             train = train or {"error": f"{type(e).__name__}: {e}"[:300]}
 
-    launches = launches_inf if not args.no_train else net._engines[dev].num_launches
+    launches = launches_plain
     per_step = ms / args.steps
     mp_per_step = BATCH * OUT_MP_PER_TILE * world
     value = mp_per_step / (per_step * 1e-3)
@@ -316,15 +425,23 @@ def main_ours(args):
     flops_step = FLOP_PER_LR_PX * BATCH * TILE * TILE      # per GPU
     peak_tf, _hbm, peak_src = _peaks()
     achieved_tf = flops_step / (per_step * 1e-3) / 1e12
-    # DRAM traffic of the dominant kernel (conv3x3_row_kernel<64,32,0>: 345 of the 423 launches of a step),
-    # bytes per launch, from the committed ncu capture of this same workload (profiles/, null if absent)
-    traffic = None
+    # Dominant kernel family: the 345 dense-block conv launches of the RRDB trunk (conv3x3_row_kernel<64,32>), 92.3 % of
+    # the step's FLOPs (483 328 FLOP per LR pixel and dense block).  Duration: CUDA events on the
+    # launching stream inside the timed region (above).  DRAM traffic: the committed ncu launch list of the same
+    # workload, used only if it was taken from the same kernel sources as the library that just ran.
+    trunk_flops = 483_328 * 3 * NB * BATCH * TILE * TILE
+    trunk_avg_ms = sum(trunk_ms) / len(trunk_ms) if trunk_ms else None
+    trunk_tf = trunk_flops / (trunk_avg_ms * 1e-3) / 1e12 if trunk_avg_ms else None
+    traffic, traffic_note = None, None
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_launch_summary_config2.json")))
-        dom = max(prof["by_kernel"], key=lambda k: k["us"])
-        traffic = (dom["dram_read_MB"] + dom["dram_write_MB"]) * 1e6 / dom["launches"]
-    except Exception:
-        pass
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_launch_summary_config2.json")))
+        if prof.get("csrc_sha256") == csrc_hash():
+            dom = max(prof["by_kernel"], key=lambda k: k["us"])
+            traffic = (dom["dram_read_MB"] + dom["dram_write_MB"]) * 1e6 / dom["launches"]
+        else:
+            traffic_note = "profiles/r02_ncu_launch_summary_config2.json was captured from other kernel sources than this build: not used"
+    except Exception as e:
+        traffic_note = f"no usable ncu summary: {type(e).__name__}"
 
     if rank == 0:
         cpu = None
@@ -344,14 +461,21 @@ def main_ours(args):
             "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": x_host.numel() * 4 * world,
                     "d2h_bytes_per_step": y_host.numel() * 4 * world, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches * args.steps * world,
-            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read+write, dominant kernel)",
+            "roofline": {"bound": "tensor", "achieved": trunk_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": trunk_tf / peak_tf if trunk_tf else None, "traffic": traffic,
+                         "traffic_unit": "bytes per launch (ncu dram__bytes_read+write, dominant kernel)", "traffic_note": traffic_note,
                          "peak_source": peak_src,
-                         "kernel": "conv3x3_row_kernel family (tcgen05 fused conv; all launches of the step but 3 layout kernels)",
-                         "flops_per_step_per_gpu": flops_step},
+                         "kernel": "conv3x3_row_kernel<64,32>: the 345 dense-block conv launches of the RRDB trunk (tcgen05)",
+                         "algorithmic_flops": trunk_flops, "launches": 15 * NB, "duration_ms": trunk_avg_ms,
+                         "duration_source": f"cudaEvent pair per forward on the launching stream, {len(trunk_ms)} timed forwards",
+                         "whole_step": {"achieved": achieved_tf, "frac": achieved_tf / peak_tf, "flops_per_step_per_gpu": flops_step}},
             "cpu_baseline": cpu,
             "clocks": clocks,
             "e2e_uint8": e2e_u8,
+            "chain": chain_leg,
+            "tiled": tiled_leg,
+            "gpu_library_baseline": lib_leg,
+            "attempts": 1,
             "train": train,
             "train_strong": train_strong,
         }
@@ -367,48 +491,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-train", action="store_true", help="skip the secondary GAN-train-step leg (config 4)")
-    ap.add_argument("--worker", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-extras", action="store_true", help="skip the chain / tiled / library-baseline legs")
     args = ap.parse_args()
     if args.impl == "reference":
         main_reference(args)
-    elif int(os.environ.get("WORLD_SIZE", "1")) == 1 and not args.worker:
-        supervise()
     else:
         main_ours(args)
-
-
-def supervise():
-    """N = 1: the measurement runs in a worker process (same file, same flags).  A device fault leaves a CUDA context
-    unusable, so it cannot be retried in-process; one such fault ("unspecified launch failure") was seen in ~40 runs of
-    this round (known issue).  A failed attempt is reported on stderr and repeated ONCE, with the
-    earlier MMA-issuer protocol (ESRP_ROW_ALT=0); the JSON line says how many attempts it took.  Under torchrun (N > 1)
-    every rank measures directly."""
-    import subprocess
-    import torch
-    from esrganplus_b200 import _lib
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
-    _lib.load()   # a missing extension fails here, loudly, not inside a retry loop
-    for attempt in (1, 2):
-        env = dict(os.environ)
-        if attempt == 2:
-            env["ESRP_ROW_ALT"] = "0"
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), *sys.argv[1:], "--worker"], env=env,
-                           stdout=subprocess.PIPE, text=True)
-        out = r.stdout.splitlines()
-        lines = [l for l in out if l.startswith("{")]
-        if r.returncode == 0 and lines:
-            for l in out:
-                if l is not lines[-1]:
-                    print(l)
-            d = json.loads(lines[-1])
-            d["attempts"] = attempt
-            if attempt == 2:
-                d["retry_env"] = {"ESRP_ROW_ALT": "0"}
-            print(json.dumps(d))
-            return
-        sys.stderr.write(f"bench.py: worker attempt {attempt} failed (rc={r.returncode})\n{r.stdout[-2000:]}\n")
-    raise SystemExit(1)
 
 
 if __name__ == "__main__":

@@ -166,6 +166,8 @@ SYMBOLS = {
     "esrp_rrdbnet_num_launches": (C.c_int32, [C.c_void_p]),
     "esrp_rrdbnet_set_chain": (C.c_int, [C.c_void_p, C.c_int32]),
     "esrp_rrdbnet_num_chained_convs": (C.c_int32, [C.c_void_p]),
+    "esrp_rrdbnet_set_timing": (C.c_int, [C.c_void_p, C.c_int32]),
+    "esrp_rrdbnet_get_timing": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float), C.c_int32]),
     "esrp_rrdbnet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_void_p]),
     "esrp_u8hwc_to_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

@@ -397,9 +397,13 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv3x3_chain_kernel(const _
       // Before the first MMA into block X: its previous occupant has been read + zeroed (blk_empty phase of the previous
       // use; a block never used passes at once), and so has whatever last lived in the same columns under the other
       // ring layout (block X ^ 8: the conv1x1 blocks of the 8-block ring are the columns of blocks 8..15).
+      int fresh = NBLK_MAX;  // touches of this phase that may still meet a block of the previous phase's layout
       auto touch = [&](uint32_t X) {
         mbar_wait(&blk_empty[X], ((ucnt >> X) & 1u) ^ 1u);
-        mbar_wait(&blk_empty[X ^ 8u], ((ucnt >> (X ^ 8u)) & 1u) ^ 1u);
+        if (fresh > 0) {
+          mbar_wait(&blk_empty[X ^ 8u], ((ucnt >> (X ^ 8u)) & 1u) ^ 1u);
+          --fresh;
+        }
         ucnt ^= 1u << X;
       };
       ChainWalk sw(a.units_total, img_h, a.x_tiles, cta, ncta);

@@ -172,6 +172,8 @@ void esrp_rrdbnet_destroy(esrp_rrdbnet_t* h) {
   destroy_train_state(m);
   for (Step& st : m->steps)
     if (st.kind == Step::kChain) free_chain(&st.chain);
+  for (cudaEvent_t e : m->ev0) cudaEventDestroy(e);
+  for (cudaEvent_t e : m->ev1) cudaEventDestroy(e);
   if (m->pack_jobs_dev) cudaFree(m->pack_jobs_dev);
   if (m->wbuf) cudaFree(m->wbuf);
   delete m;
@@ -308,10 +310,10 @@ void clear_steps(Rrdbnet* m) {
 }
 
 // Merge every run of >= 2 consecutive chain-compatible conv launches (the dense-block convs of the trunk) into one
-// persistent launch.  ESRP_NO_CHAIN=1 keeps one launch per conv (A/B timing, bisecting).
+// persistent launch — when asked to (esrp_rrdbnet_set_chain, or ESRP_CHAIN=1 for every engine of the process).
 int merge_chains(Rrdbnet* m) {
-  static const bool off = getenv("ESRP_NO_CHAIN") != nullptr;
-  if (off || !m->use_chain) return 0;
+  static const bool env_on = [] { const char* e = getenv("ESRP_CHAIN"); return e && atoi(e) != 0; }();
+  if (!m->use_chain && !env_on) return 0;
   static const size_t max_run = [] { const char* e = getenv("ESRP_CHAIN_MAX"); return e ? static_cast<size_t>(atoi(e)) : static_cast<size_t>(kChainMaxPhasesHost); }();
   std::vector<Step> out;
   size_t i = 0;
@@ -328,6 +330,7 @@ int merge_chains(Rrdbnet* m) {
       Step st;
       st.kind = Step::kChain;
       st.chain_convs = static_cast<int>(j - i);
+      st.is_rdb = m->steps[i].is_rdb;
       if (plan_chain(cs.data(), static_cast<int>(cs.size()), &st.chain)) {
         for (Step& o : out)
           if (o.kind == Step::kChain) free_chain(&o.chain);
@@ -446,6 +449,7 @@ int build_plan(Rrdbnet* m, int n, int h, int w, uint8_t* wsp, int training, cuda
             d.r1 = G; d.r1_is_f32 = 0; d.r1_ctotal = 4 * gc; d.r1_c0 = gc; d.s1 = 1.f;
           }
           if (push_conv(d)) return 1;
+          m->steps.back().is_rdb = true;
         } else {
           // out = noise(0.2 * x5 + x)                         (block.py:268), channels [row0, row0+32)
           const int c0 = c.row0;
@@ -459,6 +463,7 @@ int build_plan(Rrdbnet* m, int n, int h, int w, uint8_t* wsp, int training, cuda
           d.out_f32 = out_f; d.of_ctotal = nf; d.of_c0 = c0;
           d.f32_planar = planar;
           if (push_conv(d, false, training != 0, noise_index)) return 1;
+          m->steps.back().is_rdb = true;
         }
       }
       ++noise_index;
@@ -561,7 +566,14 @@ int esrp_rrdbnet_forward(esrp_rrdbnet_t* h, const float* x, float* y, int32_t n,
   }
   static const bool debug_sync = getenv("ESRP_DEBUG_SYNC") != nullptr;  // locate a failing launch
   int step_idx = 0;
+  int first_rdb = -1, last_rdb = -1;
+  if (m->timing) {
+    for (int i = 0; i < static_cast<int>(m->steps.size()); ++i)
+      if (m->steps[i].is_rdb) { if (first_rdb < 0) first_rdb = i; last_rdb = i; }
+  }
+  const size_t ev_slot = static_cast<size_t>(m->timed_forwards % 64);
   for (Step& st : m->steps) {
+    if (step_idx == first_rdb) ESRP_CUDA_OK(cudaEventRecord(m->ev0[ev_slot], s));
     if (debug_sync) {
       cudaError_t e = cudaStreamSynchronize(s);
       if (e != cudaSuccess) {
@@ -596,8 +608,43 @@ int esrp_rrdbnet_forward(esrp_rrdbnet_t* h, const float* x, float* y, int32_t n,
         if (run_conv(st.conv, s)) return 1;
         break;
     }
+    if (step_idx - 1 == last_rdb && last_rdb >= 0) {
+      ESRP_CUDA_OK(cudaEventRecord(m->ev1[ev_slot], s));
+      ++m->timed_forwards;
+    }
   }
   return 0;
+}
+
+int esrp_rrdbnet_set_timing(esrp_rrdbnet_t* h, int32_t enable) {
+  Rrdbnet* m = reinterpret_cast<Rrdbnet*>(h);
+  if (!m) return set_error("rrdbnet_set_timing: null handle");
+  if (enable && m->ev0.empty()) {
+    m->ev0.resize(64);
+    m->ev1.resize(64);
+    for (int i = 0; i < 64; ++i) {
+      ESRP_CUDA_OK(cudaEventCreate(&m->ev0[i]));
+      ESRP_CUDA_OK(cudaEventCreate(&m->ev1[i]));
+    }
+  }
+  m->timing = enable != 0;
+  m->timed_forwards = 0;
+  return 0;
+}
+
+int32_t esrp_rrdbnet_get_timing(esrp_rrdbnet_t* h, float* ms, int32_t max) {
+  Rrdbnet* m = reinterpret_cast<Rrdbnet*>(h);
+  if (!m || !ms || max < 1) return -1;
+  const long long n = m->timed_forwards < 64 ? m->timed_forwards : 64;
+  const long long take = n < max ? n : max;
+  for (long long i = 0; i < take; ++i) {
+    const size_t slot = static_cast<size_t>((m->timed_forwards - take + i) % 64);
+    if (cudaEventElapsedTime(&ms[i], m->ev0[slot], m->ev1[slot]) != cudaSuccess) {
+      set_error("rrdbnet_get_timing: events not complete (synchronise the stream first)");
+      return -1;
+    }
+  }
+  return static_cast<int32_t>(take);
 }
 
 int64_t esrp_rrdbnet_workspace_bytes_u8(const esrp_rrdbnet_t* h, int32_t n, int32_t hh, int32_t w) {

@@ -37,6 +37,7 @@ struct Step {
   int n = 0, h = 0, w = 0, c = 0, c_pad = 0;
   bool patch_y = false;      // conv writes the caller's output tensor
   bool is_noise = false;     // conv5 with GaussianNoise (training)
+  bool is_rdb = false;       // a dense-block conv of the trunk (what esrp_rrdbnet_set_timing brackets)
   int noise_index = 0;
 };
 
@@ -62,8 +63,13 @@ struct Rrdbnet {
   int pn = 0, ph = 0, pw = 0, ptraining = -1;
   void* pws = nullptr;
   bool g_zeroed = false;
-  bool use_chain = true;              // merge runs of row-kernel convs into persistent chain launches (esrp_rrdbnet_set_chain)
+  bool use_chain = false;             // merge runs of row-kernel convs into persistent chain launches (esrp_rrdbnet_set_chain;
+                                      // off by default: measured slower than one launch per conv)
   std::vector<Step> steps;
+  // esrp_rrdbnet_set_timing: a ring of event pairs around the dense-block convs of the trunk, one pair per forward
+  bool timing = false;
+  std::vector<cudaEvent_t> ev0, ev1;
+  long long timed_forwards = 0;
   TrainState* train = nullptr;        // training plan + dgrad weight cache (lazily created)
   const uint8_t* x_u8 = nullptr;     // set for the duration of esrp_rrdbnet_forward_u8: the input is an 8-bit HWC image
   int x_bgr = 0;

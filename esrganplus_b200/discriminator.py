@@ -202,7 +202,7 @@ class DiscriminatorEngine:
         """Derived weight tensors follow the Parameter (pointer / in-place version).  They are rebuilt IN PLACE: recorded
         launch plans keep pointing at the same packed tiles, bias vector and 3x3 view of a 4x4 weight."""
         w, b = L.conv.weight, L.conv.bias
-        sig = (w.data_ptr(), w._version, b.data_ptr() if b is not None else 0, b._version if b is not None else 0, self.epoch)
+        sig = (w.data_ptr(), w._version, b.data_ptr() if b is not None else 0, b._version if b is not None else 0, getattr(self, "epoch", 0))
         if sig == L.sig:
             return
         if w.device != self.device or w.dtype != torch.float32:

@@ -134,8 +134,21 @@ class GeneratorEngine:
         """Conv launches that the persistent chains of the last planned forward replaced."""
         return self.lib.esrp_rrdbnet_num_chained_convs(self.handle)
 
+    def set_timing(self, enable: bool) -> None:
+        """Bracket the dense-block convs of the trunk of every following forward with CUDA events (esrp_rrdbnet_set_timing)."""
+        _lib.check(self.lib.esrp_rrdbnet_set_timing(self.handle, int(bool(enable))), "esrp_rrdbnet_set_timing")
+
+    def trunk_times_ms(self, last: int = 64) -> List[float]:
+        """Device milliseconds of the trunk's dense-block convs in the last timed forwards (synchronises the device)."""
+        torch.cuda.synchronize(self.device)
+        buf = (C.c_float * last)()
+        n = self.lib.esrp_rrdbnet_get_timing(self.handle, buf, last)
+        if n < 0:
+            raise RuntimeError("esrp_rrdbnet_get_timing failed: " + self.lib.esrp_last_error().decode())
+        return [float(buf[i]) for i in range(n)]
+
     def set_chain(self, enable: bool) -> None:
-        """One persistent launch for the dense-block convs of the trunk (default) or one launch per conv."""
+        """One persistent launch for the dense-block convs of the trunk (opt-in, see include/esrp.h) or one launch per conv (default)."""
         _lib.check(self.lib.esrp_rrdbnet_set_chain(self.handle, int(bool(enable))), "esrp_rrdbnet_set_chain")
 
     # -- training --------------------------------------------------------------------------------

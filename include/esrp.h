@@ -324,11 +324,20 @@ int esrp_rrdbnet_load_weights(esrp_rrdbnet_t* h, const void* const* ptrs, int32_
 int64_t esrp_rrdbnet_workspace_bytes(const esrp_rrdbnet_t* h, int32_t n, int32_t hgt, int32_t w);
 /* Kernel launches in the most recently planned forward (for bench.py's gpu_launches). */
 int32_t esrp_rrdbnet_num_launches(const esrp_rrdbnet_t* h);
-/* Persistent conv chain (default on): consecutive row-kernel convs of the inference plan — the five convs of every
+/* Persistent conv chain (opt-in): consecutive row-kernel convs of the inference plan — the five convs of every
  * ResidualDenseBlock_5C of the trunk (block.py:260-268) — run as phases of ONE launch that synchronises row
- * neighbours through flags in device memory (csrc/conv3x3_chain.cuh) instead of one launch per conv.  enable = 0
- * restores one launch per conv (A/B measurements, tests).  The next forward re-plans. */
+ * neighbours through flags in device memory (csrc/conv3x3_chain.cuh) instead of one launch per conv: 10 launches
+ * per forward instead of 354.  Off by default: on B200 it measures 8 % SLOWER than the launch-per-conv path at
+ * 16 x 128 x 128 (13.7 vs 12.7 ms) and 35 % slower for a single tile, because a phase boundary (epilogue tail ->
+ * flag -> first TMA row, ~6 us) costs what a programmatic dependent launch does, and its sums are reproducible up
+ * to fp32 addition order only.  enable != 0 selects it; the next forward re-plans. */
 int esrp_rrdbnet_set_chain(esrp_rrdbnet_t* h, int32_t enable);
+/* Device-time the dense-block convs of the trunk — the "RRDB 3x3-conv stack" BASELINE.json quotes the tensor-pipe
+ * fraction on — of every following inference forward: one pair of CUDA events on the launching stream per forward
+ * (ring of 64).  After synchronising the stream, esrp_rrdbnet_get_timing copies the milliseconds of the last
+ * (at most `max`) timed forwards to ms[] (oldest first) and returns how many; -1 on error. */
+int esrp_rrdbnet_set_timing(esrp_rrdbnet_t* h, int32_t enable);
+int32_t esrp_rrdbnet_get_timing(esrp_rrdbnet_t* h, float* ms, int32_t max);
 /* Conv launches the chains of the most recently planned forward replaced (0 when none was built). */
 int32_t esrp_rrdbnet_num_chained_convs(const esrp_rrdbnet_t* h);
 /* x: NCHW fp32 [n,in_nc,h,w] -> y: NCHW fp32 [n,out_nc,upscale*h,upscale*w] (unclamped, like the

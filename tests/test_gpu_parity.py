@@ -435,16 +435,13 @@ def test_config2_full_size_properties(cuda_dev):
     xd = x.to(cuda_dev)
     y = net(xd)
     assert y.shape == (16, 3, 512, 512) and torch.isfinite(y).all()
-    # Run-to-run: the persistent chain hands whole rows from one MMA issuer thread to the other in order, so the
-    # accumulation order is fixed and a forward reproduces bit for bit.
+    # Run-to-run and batch-composition stability of the default (launch-per-conv) path: the MMA issue order is fixed
+    # by the issuers' turn tokens, so a forward reproduces bit for bit.
     assert torch.equal(net(xd), y), "run-to-run"
-    # Batch composition changes which rows a CTA owns and (a single tile has fewer rows than SMs) which launches are
-    # chained; the taps of a row are then added in another order, and through the bf16 rounding of 69 chained blocks
-    # that moves single values by up to the parity tolerance itself: bound the rms 10x tighter, the maximum 2x.
+
     def _same(a, b, what):
         d = (a - b).abs().max().item() / y.std().item()
-        rms = (a - b).pow(2).mean().sqrt().item() / y.std().item()
-        assert d <= NET_REL_TOL / 2 and rms <= NET_REL_TOL / 10, f"{what}: max {d:.3e} rms {rms:.3e}"
+        assert d <= NET_REL_TOL / 10, f"{what}: {d:.3e}"
     # tiles are independent units: a tile's result does not depend on its batch mates
     perm = torch.arange(15, -1, -1)
     _same(net(xd[perm])[perm], y, "batch permutation")
@@ -463,8 +460,17 @@ def test_config2_full_size_properties(cuda_dev):
 CHAIN_SHAPES = [(3, 37, 100), (2, 70, 128), (1, 9, 300), (5, 3, 130), (4, 64, 65), (2, 1, 128), (7, 128, 128)]
 
 
+def _rel_rms(a, b):
+    s = b.std().item()
+    return (a - b).abs().max().item() / s, (a - b).pow(2).mean().sqrt().item() / s
+
+
 @pytest.mark.parametrize("shape", CHAIN_SHAPES)
 def test_chain_matches_per_conv_launches_and_oracle(cuda_dev, shape):
+    """The opt-in persistent chain computes what the launch-per-conv path computes.  Its three issuer threads reach the
+    tensor pipe in no fixed order, so two runs (and the two paths) agree up to fp32 addition order, which the bf16
+    rounding of every conv output amplifies to what either path differs from a storage-precision emulation by
+    (tools/chain_diag.py: rms 1e-3 of std at nb = 1, maximum 1e-2): bound the rms 10x below the parity tolerance."""
     n, h, w = shape
     nb = 2
     sd = O.synth_state_dict_g(3, 3, 64, nb, seed=41)
@@ -473,40 +479,43 @@ def test_chain_matches_per_conv_launches_and_oracle(cuda_dev, shape):
     x = torch.rand(n, 3, h, w, generator=g)
     xd = x.to(cuda_dev)
     eng = net._engine_for(cuda_dev)
-    y = net(xd)
-    assert eng.num_chained_convs >= 4 * 3 * nb, (eng.num_chained_convs, eng.num_launches)
-    # the two issuer threads hand whole rows over in order: the accumulation order is fixed, results reproduce bit for bit
-    for _ in range(3):
-        assert torch.equal(net(xd), y), "chain results must be run-to-run identical"
-    eng.set_chain(False)
     y_plain = net(xd)
-    assert eng.num_chained_convs == 0
+    assert eng.num_chained_convs == 0, "the chain is opt-in"
+    assert torch.equal(net(xd), y_plain), "the launch-per-conv path reproduces bit for bit"
     eng.set_chain(True)
-    assert torch.equal(net(xd), y)
-    # the two paths add the taps of a row in another order; through the bf16 roundings of every conv output that is
-    # worth what either path differs from the storage-precision emulation by (tools/chain_diag.py: rms 1e-3 of std at
-    # nb = 1), far below the parity bound
-    d = (y - y_plain).abs().max().item() / y_plain.std().item()
-    rms = (y - y_plain).pow(2).mean().sqrt().item() / y_plain.std().item()
-    assert d <= NET_REL_TOL and rms <= NET_REL_TOL / 10, f"chain vs one launch per conv: max {d:.3e} rms {rms:.3e}"
-    if n * h * w <= 3 * 37 * 130:
-        _net_close(y.cpu(), O.rrdbnet_forward(x, sd, nb), f"chain {shape}")
+    try:
+        y = net(xd)
+        assert eng.num_chained_convs >= 4 * 3 * nb, (eng.num_chained_convs, eng.num_launches)
+        for _ in range(3):
+            d, rms = _rel_rms(net(xd), y)
+            assert d <= NET_REL_TOL and rms <= NET_REL_TOL / 10, f"chain run-to-run: max {d:.3e} rms {rms:.3e}"
+        d, rms = _rel_rms(y, y_plain)
+        assert d <= NET_REL_TOL and rms <= NET_REL_TOL / 10, f"chain vs one launch per conv: max {d:.3e} rms {rms:.3e}"
+        if n * h * w <= 3 * 37 * 130:
+            _net_close(y.cpu(), O.rrdbnet_forward(x, sd, nb), f"chain {shape}")
+    finally:
+        eng.set_chain(False)
 
 
 def test_chain_nb23_many_phases_back_to_back(cuda_dev):
     """345 phases per launch, 12 launches back to back (flags are reset per launch), 6 images of 96 rows so that CTA
-    ranges cross image boundaries: every result identical, and one tile checked against the fp32 oracle."""
+    ranges cross image boundaries; one tile checked against the fp32 oracle."""
     sd = O.synth_state_dict_g(3, 3, 64, 23, seed=31)
     net = _make(E.RRDBNet, sd, 64, 23, cuda_dev)
     g = torch.Generator().manual_seed(6)
     x = torch.rand(6, 3, 96, 128, generator=g)
     xd = x.to(cuda_dev)
     eng = net._engine_for(cuda_dev)
+    eng.set_chain(True)
     y = net(xd)
     assert eng.num_chained_convs == 345 and eng.num_launches <= 12, (eng.num_chained_convs, eng.num_launches)
     for _ in range(11):
-        assert torch.equal(net(xd), y)
+        d, rms = _rel_rms(net(xd), y)
+        assert d <= NET_REL_TOL and rms <= NET_REL_TOL / 10, f"run-to-run: max {d:.3e} rms {rms:.3e}"
     _net_close(net(xd[2:3]).cpu(), O.rrdbnet_forward(x[2:3], sd, 23), "chain nb23 tile 2")
+    eng.set_chain(False)
+    d, rms = _rel_rms(net(xd), y)
+    assert d <= NET_REL_TOL and rms <= NET_REL_TOL / 10, f"chain vs plain at nb=23: max {d:.3e} rms {rms:.3e}"
 
 
 def test_tiled_inference_matches_oracle_per_crop(cuda_dev):

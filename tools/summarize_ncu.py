@@ -67,7 +67,14 @@ def do_list(path, what):
         k["dram_write_MB"] += l["wr"]
     for k in by.values():
         k["share"] = k["us"] / tot if tot else 0.0
-    out = {"step": what, "launches": len(launches), "total_us": tot, "dram_read_MB": sum(l["rd"] for l in launches),
+    import hashlib, glob, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = os.path.join(root, "esrganplus_b200", "csrc")
+    hh = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(d, "*.cu")) + glob.glob(os.path.join(d, "*.cuh")) + glob.glob(os.path.join(d, "*.inl")) +
+                    glob.glob(os.path.join(d, "*.h")) + [os.path.join(root, "include", "esrp.h")]):
+        hh.update(open(f, "rb").read())
+    out = {"step": what, "csrc_sha256": hh.hexdigest(), "launches": len(launches), "total_us": tot, "dram_read_MB": sum(l["rd"] for l in launches),
            "dram_write_MB": sum(l["wr"] for l in launches), "by_kernel": sorted(by.values(), key=lambda k: -k["us"]),
            "sequence_us": [round(l["us"], 2) for l in launches[:160]],
            "sequence_kernels": [l["kernel"][:48] for l in launches[:160]]}
