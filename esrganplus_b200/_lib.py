@@ -183,6 +183,19 @@ SYMBOLS = {
     "esrp_rrdbnet_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p,
                                         C.c_void_p]),
     "esrp_rrdbnet_train_num_launches": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "esrp_adam_flat": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_double,
+                                 C.c_double, C.c_double, C.c_int64, C.c_void_p]),
+    "esrp_ragan_bce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    "esrp_l1_loss_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "esrp_lrhr_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "esrp_sizeof_lrhr_job": (C.c_int32, []),
+    "esrp_graph_begin": (C.c_int, [C.c_void_p]),
+    "esrp_graph_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "esrp_graph_abort": (C.c_int, [C.c_void_p]),
+    "esrp_graph_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "esrp_graph_destroy": (None, [C.c_void_p]),
+    "esrp_memset_zero": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
 }
 
 _lib = None

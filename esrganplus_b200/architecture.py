@@ -106,9 +106,17 @@ class _GeneratorBase(_NativeWeights, nn.Module):
 
     def noise_seed(self) -> int:
         """Philox key for this forward: torch's global seed mixed with a per-module call counter, so
-        `torch.manual_seed` reproduces a training run (the reference draws from the global stream)."""
+        `torch.manual_seed` reproduces a training run (the reference draws from the global stream), and with the
+        data-parallel rank: replicas seeded identically must not draw the same noise for their different samples
+        (per-rank Philox offset = f(rank, step))."""
         object.__setattr__(self, "_step", self._step + 1)
-        return (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._step) & 0xFFFFFFFFFFFFFFFF
+        rank = 0
+        if getattr(self, "_dp_group", False) is not False:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                g = self._dp_group
+                rank = dist.get_rank(None if g is True else g)
+        return (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._step + rank * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
 
     def forward_uint8(self, img: torch.Tensor, bgr: bool = True) -> torch.Tensor:
         """Not part of the reference surface: 8-bit images in, 8-bit images out, with the host

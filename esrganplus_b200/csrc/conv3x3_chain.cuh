@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv3x3_chain_kernel(const _
     for (int i = 0; i < NBLK_MAX; ++i) {
       mbar_init(&blk_full[i], kChainIssuers);
       mbar_init(&blk_empty[i], 4);
+      mbar_arrive_cnt(&blk_empty[i], 4);  // phase 0 = "the block is free": complete from the start
     }
     mbar_init(wfull, 1);
     mbar_init(wfree, kChainIssuers);
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv3x3_chain_kernel(const _
     constexpr uint32_t ID_FULL = umma_idesc_bf16_m128(3 * BN);
     const uint32_t idesc_aux = umma_idesc_bf16_m128(BN);
     uint32_t fmask = 0;  // per tile: parity of its next full_bar phase
-    uint32_t ucnt = 0;   // per block: use count & 1 (the release of use c completes blk_empty phase c)
+    uint32_t ucnt = 0;   // per block: use count & 1 (phase 0 of blk_empty is complete from the start, the release of use c completes phase c + 1)
     for (int ph = 0; ph < nph; ++ph) {
       const ChainPhaseC& P = a.ph[ph];
       const int nsl = P.nsl;
@@ -394,14 +395,14 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv3x3_chain_kernel(const _
       bool first_row = true;
       int slot = 0, t = 0;
       uint32_t O0 = 0;
-      // Before the first MMA into block X: its previous occupant has been read + zeroed (blk_empty phase of the previous
-      // use; a block never used passes at once), and so has whatever last lived in the same columns under the other
+      // Before the first MMA into block X: its previous occupant has been read + zeroed (the blk_empty phase its previous
+      // release completed; phase 0 is complete from the start), and so has whatever last lived in the same columns under the other
       // ring layout (block X ^ 8: the conv1x1 blocks of the 8-block ring are the columns of blocks 8..15).
       int fresh = NBLK_MAX;  // touches of this phase that may still meet a block of the previous phase's layout
       auto touch = [&](uint32_t X) {
-        mbar_wait(&blk_empty[X], ((ucnt >> X) & 1u) ^ 1u);
+        mbar_wait(&blk_empty[X], (ucnt >> X) & 1u);
         if (fresh > 0) {
-          mbar_wait(&blk_empty[X ^ 8u], ((ucnt >> (X ^ 8u)) & 1u) ^ 1u);
+          mbar_wait(&blk_empty[X ^ 8u], (ucnt >> (X ^ 8u)) & 1u);
           --fresh;
         }
         ucnt ^= 1u << X;

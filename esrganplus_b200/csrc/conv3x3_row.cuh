@@ -42,6 +42,9 @@
 //             nsl*i .. nsl*i+nsl-1 walk the same rows with the weights / bias / channel offsets of their
 //             slice, so the rows are fetched from DRAM once and every CTA owns nsl times more rows.
 #pragma once
+#ifndef ESRP_SYNCCHECK_PAD
+#define ESRP_SYNCCHECK_PAD 0  // experiment (tools/gpu_r2_p.sh): move tok[] off shared-memory offset 0x148
+#endif
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -149,8 +152,8 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
   uint64_t* blk_full = full_bar + kMaxStages;               // [kMaxBlocks] block complete (2 issuer commits)
   uint64_t* blk_empty = blk_full + kMaxBlocks;              // [kMaxBlocks] block read + zeroed (4 warps)
   uint64_t* wfull = blk_empty + kMaxBlocks;                 // [1]
-  uint64_t* tok = wfull + 1;                                // [2] issue turn: tok[w] = "warp w may issue"
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tok + 2);
+  uint64_t* tok = wfull + (ESRP_SYNCCHECK_PAD ? 2 : 1);     // [2] issue turn: tok[w] = "warp w may issue"
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + 512);  // (its own 128-byte line: tcgen05.alloc writes it asynchronously)
   uint32_t* buf_bar = tmem_holder + 1;                      // [kMaxStages] producer: barrier/parity that
   uint32_t* buf_par = buf_bar + kMaxStages;                 // [kMaxStages]   frees each row buffer
   float* bias_s = reinterpret_cast<float*>(smem + 1024);    // [BN]
@@ -183,10 +186,13 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
       // row-alternating issue (row_alt == 2): + one plain arrival of the warp that does NOT issue the completing row
       mbar_init(&blk_full[i], p.row_alt == 2 ? kRowMmaWarps + 1 : kRowMmaWarps);
       mbar_init(&blk_empty[i], 4);
+      mbar_arrive_cnt(&blk_empty[i], 4);  // phase 0 = "the block is free": complete from the start (no wait relies on the
+                                          // parity of a phase that never existed; compute-sanitizer synccheck flags those)
     }
     mbar_init(wfull, 1);
     mbar_init(&tok[0], 1);
     mbar_init(&tok[1], 1);
+    mbar_arrive(&tok[0]);                 // warp 0 holds the first turn
     fence_barrier_init();
   }
   if (warp == kRowEpiWarps + 1) {
@@ -288,10 +294,10 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
         // blocks first touched by this input row must have been read + zeroed by their previous occupant
         const uint32_t On = O0 + k + 2;  // output row r+1 (ky = 0): always new
         if (k == 0) {
-          mbar_wait(&blk_empty[pos(O0)], use(O0) ^ 1);
-          mbar_wait(&blk_empty[pos(O0 + 1)], use(O0 + 1) ^ 1);
+          mbar_wait(&blk_empty[pos(O0)], use(O0));
+          mbar_wait(&blk_empty[pos(O0 + 1)], use(O0 + 1));
         }
-        mbar_wait(&blk_empty[pos(On)], use(On) ^ 1);
+        mbar_wait(&blk_empty[pos(On)], use(On));
         tcgen05_fence_after();
         // accumulator = blocks pos(On), +1, +2; split in two MMAs where it straddles the end of the ring
         const uint32_t P = pos(On);
@@ -311,7 +317,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
           // from the issuer of its middle row r (commits only track the committing thread's MMAs; rows r-1 and r+1
           // belong to the same warp).  Segment ends: the missing contributor's commit is issued by the same thread.
           if ((I & 1u) == static_cast<uint32_t>(mw)) {
-            mbar_wait(&tok[mw], tph ^ (mw == 0 ? 1u : 0u));
+            mbar_wait(&tok[mw], tph);
             if (elect_one()) {
               uint32_t al = a_lo, bl = w_lo0;
               for (int c = 0; c < nfull; ++c, al += chunk_step, bl += w_step) {
@@ -376,7 +382,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
           if (++b == D) { b = 0; fph ^= 1; a_lo = a_lo0; }
           continue;
         }
-        mbar_wait(&tok[mw], tph ^ (mw == 0 ? 1u : 0u));
+        mbar_wait(&tok[mw], tph);
         if (elect_one()) {
           uint32_t al = a_lo, bl = w_lo0;
           if (nB == 0) {

@@ -210,10 +210,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     for (int i = 0; i < S; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
+      mbar_arrive(&empty_bar[i]);  // phase 0 = "the stage is free": complete from the start (no wait relies on the parity
+                                   // of a phase that never existed; compute-sanitizer synccheck flags those as missing init)
     }
     for (int i = 0; i < ESRP_MAX_MT; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 32 * kNumEpiWarps);
+      mbar_arrive_cnt(&acc_empty[i], 32 * kNumEpiWarps);  // phase 0 = "the accumulator slot is free"
     }
     mbar_init(wfull, 1);
     fence_barrier_init();
@@ -247,7 +250,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
         for (int c = 0; c < p.num_chunks; ++c, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_wait(&empty_bar[s], ph);
           trace_ev(p, 0, tn);
           uint8_t* st = stage0 + static_cast<size_t>(s) * stage_bytes;
           mbar_arrive_expect_tx(&full_bar[s],
@@ -287,7 +290,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
         const bool aux_c = c < p.aux_chunks;
         for (int m = 0; m < p.mt; ++m) {
           if (c == 0) {
-            mbar_wait(&acc_empty[m], accph ^ 1);
+            mbar_wait(&acc_empty[m], accph);
             tcgen05_fence_after();
           }
           const bool leader = elect_one();

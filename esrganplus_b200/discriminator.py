@@ -41,14 +41,21 @@ SLICE = 32            # output channels per launch
 MAX_CHUNKS = {_lib.LAYOUT_ROW: 3, _lib.LAYOUT_TILE: _lib.ESRP_MAX_CHUNKS}   # K chunks per launch (the row kernel keeps its weights resident in shared memory, the tile kernel streams them)
 
 
-_STREAM = [0]
+_STREAM = [None]
+import os as _os
+_USE_GRAPHS = _os.environ.get("ESRP_D_GRAPH", "1") != "0"   # replay discriminator passes as CUDA graphs (0: call by call)
+
+
+class _StreamArg(int):
+    """A cudaStream_t value that recorded call lists can recognise (and re-target when a list is captured into a CUDA
+    graph on the library's own capture stream: the legacy default stream torch normally runs on cannot be captured)."""
 
 
 def _stream(refresh: bool = False) -> int:
     """cudaStream_t of torch's current stream.  torch.cuda.current_stream() costs ~14 us, a forward makes ~150 launches:
     the engine refreshes the cached handle once per forward / backward call."""
     if refresh:
-        _STREAM[0] = torch.cuda.current_stream().cuda_stream
+        _STREAM[0] = _StreamArg(torch.cuda.current_stream().cuda_stream)
     return _STREAM[0]
 
 
@@ -112,6 +119,19 @@ class _Plan:
         self.bwd: Dict[tuple, tuple] = {}
         self.dout_buf: Optional[torch.Tensor] = None
         self.busy = False
+        # CUDA-graph replay (esrp_graph_*): the recorded call list captured once, then one launch per pass
+        self.x_in: Optional[torch.Tensor] = None      # plan-owned copy of the caller's input (its address is baked into the graph)
+        self.fwd_graph = None                         # cudaGraphExec_t, or False when capture failed (plain replay then)
+        self.bwd_graph: Dict[tuple, object] = {}
+
+    def __del__(self):
+        try:
+            lib = _lib.load()
+            for g in [self.fwd_graph] + list(self.bwd_graph.values()):
+                if g:
+                    lib.esrp_graph_destroy(g)
+        except Exception:
+            pass
 
 
 class _Lease:
@@ -135,8 +155,10 @@ class DiscriminatorEngine:
         self.plans: Dict[tuple, List[_Plan]] = {}
         self.nside = 4
         self.side = (C.c_void_p * self.nside)()
+        self.cap = (C.c_void_p * 1)()   # capture stream of the CUDA-graph replays
         with torch.cuda.device(device):
             _lib.check(self.lib.esrp_streams_create(self.nside, self.side), "esrp_streams_create")
+            _lib.check(self.lib.esrp_streams_create(1, self.cap), "esrp_streams_create")
         self._rec: Optional[list] = None     # call list being recorded
         self._keep: Optional[list] = None    # keep-alive list of the plan being recorded
         self._ptr_sig = None
@@ -177,6 +199,29 @@ class DiscriminatorEngine:
             rc = fn(*args)
             if what is not None and rc != 0:
                 _lib.check(rc, what)
+
+    def _capture(self, calls, stream: int):
+        """The recorded call list as an executable CUDA graph (None if graphs are switched off, False if capture fails: the
+        caller then keeps replaying call by call).  ~150 ctypes calls of 10-15 us each become one launch.  The list is
+        replayed onto the engine's own capture stream (every `_StreamArg` argument re-targeted); the graph is then launched
+        on the caller's stream."""
+        if not _USE_GRAPHS:
+            return None
+        if any(what is None for _, _, what in calls):
+            return False   # a framework-level op in the list cannot be re-targeted
+        lib = self.lib
+        cap = self.cap[0]
+        if lib.esrp_graph_begin(cap) != 0:
+            return False
+        try:
+            self._replay([(fn, tuple(cap if isinstance(a, _StreamArg) else a for a in args), what) for fn, args, what in calls])
+        except Exception:
+            lib.esrp_graph_abort(cap)
+            return False
+        exe = C.c_void_p()
+        if lib.esrp_graph_end(cap, C.byref(exe)) != 0 or not exe.value:
+            return False
+        return exe
 
     def _acquire(self, module: nn.Module, n: int) -> _Plan:
         # recorded calls bake in the addresses of Parameters / buffers (Linear weights, BatchNorm vectors): a plan is
@@ -320,8 +365,17 @@ class DiscriminatorEngine:
                 self._rec = self._keep = None
         else:
             fn, args, what = plan.fwd[plan.x_idx]
-            plan.fwd[plan.x_idx] = (fn, (x.data_ptr(),) + args[1:], what)
-            self._replay(plan.fwd)
+            if plan.fwd_graph is None:
+                if plan.x_in is None:
+                    plan.x_in = torch.empty_like(x)
+                plan.fwd[plan.x_idx] = (fn, (plan.x_in.data_ptr(),) + args[1:], what)
+                plan.fwd_graph = self._capture(plan.fwd, plan.stream)
+            if plan.fwd_graph:
+                plan.x_in.copy_(x)
+                _lib.check(self.lib.esrp_graph_launch(plan.fwd_graph, plan.stream), "esrp_graph_launch")
+            else:
+                plan.fwd[plan.x_idx] = (fn, (x.data_ptr(),) + args[1:], what)
+                self._replay(plan.fwd)
             if plan.nbt:
                 torch._foreach_add_(plan.nbt, 1)
         return plan.out.clone(), (_Lease(plan) if lease else None)
@@ -425,7 +479,7 @@ class DiscriminatorEngine:
         n, gh, gw, _ = dz.shape
         nu = ng * nblk
         acc = self._t(torch.empty(nu * ACC_BLOCK + nblk * 64, dtype=torch.float32, device=self.device))
-        self._op(acc.zero_)
+        self._c(self.lib.esrp_memset_zero, "esrp_memset_zero", acc.data_ptr(), acc.numel() * acc.element_size(), _stream())
         units, scat = units0.copy(), scat0.copy()
         accp = acc.data_ptr()
         bias_base = accp + 4 * nu * ACC_BLOCK
@@ -448,7 +502,7 @@ class DiscriminatorEngine:
             self._c(self.lib.esrp_conv3x3_wgrad, "esrp_conv3x3_wgrad", part.ctypes.data_as(C.POINTER(_lib.WgradUnit)), cnt, n, gh, gw,
                     0, st)
         if L.k == 3 and L.cin % 32:
-            self._op(dw.zero_)  # (never the case for D_VGG_128 beyond layer 0, whose 3 real channels are all written)
+            self._c(self.lib.esrp_memset_zero, "esrp_memset_zero", dw.data_ptr(), dw.numel() * dw.element_size(), _stream())  # (never the case for D_VGG_128 beyond layer 0, whose 3 real channels are all written)
         self._t(scat)
         self._c(self.lib.esrp_wgrad_scatter, "esrp_wgrad_scatter", scat.ctypes.data_as(C.POINTER(_lib.ScatterEntry)), len(scat), st)
 
@@ -493,6 +547,9 @@ class DiscriminatorEngine:
         gradients are views of a fresh copy of the plan's flat buffer, in named_parameters() order."""
         names, plist = _named_params(module)
         n = plan.saved[-1]["n"]
+        if _stream(refresh=True) != plan.stream:
+            raise RuntimeError("Discriminator_VGG_128 backward must run on the CUDA stream its forward ran on (the plan's "
+                               "buffers and recorded launches belong to that stream)")
         if plan.dout_buf is None:
             plan.dout_buf = torch.empty((n, self.fc1.out_features), dtype=torch.float32, device=self.device)
         plan.dout_buf.copy_(dout)
@@ -506,7 +563,13 @@ class DiscriminatorEngine:
             finally:
                 self._rec = self._keep = None
         else:
-            self._replay(ent[0])
+            gr = plan.bwd_graph.get(key)
+            if gr is None:
+                gr = plan.bwd_graph[key] = self._capture(ent[0], plan.stream)
+            if gr:
+                _lib.check(self.lib.esrp_graph_launch(gr, plan.stream), "esrp_graph_launch")
+            else:
+                self._replay(ent[0])
         _, dx, flatg, sizes = ent
         grads, flat = [None] * len(names), None
         if need_params:

@@ -237,6 +237,64 @@ int esrp_linear_bwd_f32(const float* dy, const float* yout_act, const float* x, 
 int esrp_streams_create(int32_t n, void** out_streams);
 int esrp_streams_fork(void* main_stream, void* const* sides, int32_t n);
 int esrp_streams_join(void* main_stream, void* const* sides, int32_t n);
+/* ---------------------------------------------------------------------------------------------
+ * Solver arithmetic between the passes (csrc/esrp_solver.cu)
+ * ------------------------------------------------------------------------------------------- */
+/* torch.optim.Adam (SRRaGAN_model.py:82-89: lr, betas, weight_decay as L2, eps 1e-8, no amsgrad) over flat storage, one
+ * kernel: p, g, m (exp_avg), v (exp_avg_sq) are device arrays of n floats (n % 4 == 0, 16-byte aligned), `step` counts
+ * from 1 (bias corrections 1 - beta^step, evaluated in double like torch; hyper-parameters are doubles for the same
+ * reason: 1 - beta2 must round to float once).  The learning rate of the step comes from the caller (MultiStepLR,
+ * SRRaGAN_model.py:91-95, is a host-side schedule). */
+int esrp_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps,
+                   double weight_decay, int64_t step, void* stream);
+/* Relativistic-average GAN loss terms (SRRaGAN_model.py:133-136,151-154 with GANLoss('vanilla') = BCEWithLogits,
+ * loss.py:11-38): A = BCE(pred_real - mean(pred_fake), t_real), B = BCE(pred_fake - mean(pred_real), t_fake) over n
+ * logits each.  out4 = {A, B, mean(pred_real), mean(pred_fake)}; dA_* / dB_* [n]: gradients of the two terms w.r.t. the
+ * raw logits (through the means).  One single-block launch. */
+int esrp_ragan_bce(const float* pred_real, const float* pred_fake, int32_t n, float t_real, float t_fake, float* out4,
+                   float* dA_dreal, float* dA_dfake, float* dB_dreal, float* dB_dfake, void* stream);
+/* nn.L1Loss (SRRaGAN_model.py:31-39,123): *loss = mean |a - b| over n floats (n % 4 == 0), grad (optional) = d loss / d a
+ * = sign(a - b) / n.  scratch: one device double. */
+int esrp_l1_loss_grad(const float* a, const float* b, int64_t n, float* grad, float* loss, double* scratch, void* stream);
+/* Capture everything enqueued on `stream` (and on streams forked from it with esrp_streams_fork / joined with
+ * esrp_streams_join) between begin and end into an executable CUDA graph; launch replays it with one call.  The
+ * discriminator's passes are lists of ~150 recorded C-ABI calls each: replayed as graphs they cost one launch of host
+ * time.  abort ends a capture after a failed call. */
+int esrp_graph_begin(void* stream);   /* (not the legacy default stream: it cannot be captured) */
+int esrp_graph_end(void* stream, void** out_exec);
+int esrp_graph_abort(void* stream);
+int esrp_graph_launch(void* exec, void* stream);
+void esrp_graph_destroy(void* exec);
+/* cudaMemsetAsync(p, 0, bytes) as a recordable / capturable C-ABI call. */
+int esrp_memset_zero(void* p, int64_t bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Training data path on the device (csrc/esrp_data.cu)
+ * ------------------------------------------------------------------------------------------- */
+/* One training sample: an HR image resident on the device as the reference reads it (cv2: uint8, HWC, BGR) plus the
+ * decisions the reference draws on the host (LRHR_dataset.py:99-100 crop offsets in LR pixels, util.py:96-98 flips /
+ * rotation) and the MATLAB-bicubic tables of its height and width (util.py:219-274 calculate_weights_indices for
+ * scale 1/s: wh [h/s][ph] weights, ih [h/s] first index of each window in the symmetric-padded image, sym_hs = rows
+ * mirrored in front; same for the width).  All pointers are device pointers. */
+typedef struct {
+  const uint8_t* img;
+  int32_t h, w;
+  int32_t rnd_h, rnd_w;
+  int32_t hflip, vflip, rot90;
+  const float* wh;
+  const int32_t* ih;
+  const float* ww;
+  const int32_t* iw;
+  int32_t ph, pw, sym_hs, sym_ws;
+} esrp_lrhr_job_t;
+int32_t esrp_sizeof_lrhr_job(void);
+/* LRHR_dataset.py:83-121 with on-the-fly LR for `count` samples (jobs_dev: device array): lr_out [count,3,hr_size/s,hr_size/s],
+ * hr_out [count,3,hr_size,hr_size] fp32 RGB CHW in [0,1] — util.imresize_np(img/255, 1/s) restricted to the crop, the HR
+ * crop, util.augment, the BGR->RGB swap and the HWC->CHW transpose in one launch (one CTA per sample).  xw_max: an upper
+ * bound of the padded columns one LR crop row reads: (hr_size/s - 1) * s + pw + 2. */
+int esrp_lrhr_batch(const esrp_lrhr_job_t* jobs_dev, int32_t count, int32_t scale, int32_t hr_size, int32_t xw_max, float* lr_out,
+                    float* hr_out, void* stream);
+
 /* nn.Linear (+ optional LeakyReLU 0.2): y[b,o] = sum_k x[b,k] w[o,k] + bias[o]  (architecture.py:122-123). */
 int esrp_linear_f32(const float* x, const float* w, const float* bias, float* y, int32_t b, int32_t k, int32_t o,
                     int32_t act, void* stream);

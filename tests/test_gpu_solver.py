@@ -1,0 +1,118 @@
+"""The native solver arithmetic (esrganplus_b200/solver.py over csrc/esrp_solver.cu) against
+what the reference runs: torch.optim.Adam + lr_scheduler.MultiStepLR (SRRaGAN_model.py:82-95), BCEWithLogits relativistic
+terms (:133-136,151-154, loss.py:11-38) and nn.L1Loss (:123), all on the same device in fp32."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import esrganplus_b200 as E
+from esrganplus_b200.gan_step import GanTrainStep
+from esrganplus_b200.solver import FlatAdam, l1_loss, ragan_bce_terms
+from oracle import esrgan_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _toy_params(dev, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    shapes = [(32, 3, 3, 3), (32,), (32, 32, 1, 1), (7,), (64, 96, 3, 3), (1, 100), (1,)]   # sizes that need 16-byte padding too
+    return [torch.nn.Parameter(torch.randn(s, generator=g).to(dev)) for s in shapes]
+
+
+@pytest.mark.parametrize("flat_grads", [False, True])
+def test_flat_adam_matches_torch_adam_step_for_step(cuda_dev, flat_grads):
+    pa, pb = _toy_params(cuda_dev), _toy_params(cuda_dev)
+    ref = torch.optim.Adam(pa, lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+    opt = FlatAdam(pb, lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+    sch_a = torch.optim.lr_scheduler.MultiStepLR(ref, [2, 4], 0.5)
+    sch_b = torch.optim.lr_scheduler.MultiStepLR(opt, [2, 4], 0.5)    # the reference's scheduler drives it unchanged
+    g = torch.Generator().manual_seed(1)
+    offs, off = [], 0
+    for p in pb:
+        offs.append(off)
+        off += (p.numel() + 3) // 4 * 4
+    for it in range(6):
+        grads = [torch.randn(p.shape, generator=g).to(cuda_dev) * (0.1 + it) for p in pa]
+        flat = torch.zeros(off, device=cuda_dev)
+        for p, q, gr, o in zip(pa, pb, grads, offs):
+            p.grad = gr.clone()
+            if flat_grads:   # the layout the native backward passes produce: views of one padded flat buffer
+                flat[o:o + q.numel()].copy_(gr.flatten())
+                q.grad = flat[o:o + q.numel()].view(q.shape)
+            else:
+                q.grad = gr.clone()
+        ref.step(); opt.step(); sch_a.step(); sch_b.step()
+        assert ref.param_groups[0]["lr"] == pytest.approx(opt.param_groups[0]["lr"])
+        for i, (p, q) in enumerate(zip(pa, pb)):
+            d = (p.detach() - q.detach()).abs().max().item()
+            assert d <= 2e-6 * (1.0 + p.detach().abs().max().item()), (it, i, d)
+    if flat_grads:
+        assert opt._flat_g is None, "gradients that already are views of one flat buffer must not be gathered"
+    sa, sb = ref.state_dict()["state"], opt.state_dict()["state"]
+    for i in range(len(pa)):
+        for key in ("exp_avg", "exp_avg_sq"):   # (torch's lerp / addcmul and the kernel's fused multiply-adds round differently)
+            a, b = sa[i][key], sb[i][key]
+            assert (a - b).abs().max().item() <= 2e-6 * a.abs().max().item(), (i, key, (a - b).abs().max().item())
+        assert float(sb[i]["step"]) == 6.0
+
+
+@pytest.mark.parametrize("n", [1, 3, 32, 500])
+def test_ragan_bce_terms_match_torch(cuda_dev, n):
+    g = torch.Generator().manual_seed(n)
+    r0, f0 = torch.randn(n, 1, generator=g) * 3, torch.randn(n, 1, generator=g) * 3 + 0.5
+    for t_real, t_fake in ((1.0, 0.0), (0.0, 1.0)):
+        ra, fa = r0.clone().to(cuda_dev).requires_grad_(True), f0.clone().to(cuda_dev).requires_grad_(True)
+        rb, fb = r0.clone().to(cuda_dev).requires_grad_(True), f0.clone().to(cuda_dev).requires_grad_(True)
+        A = F.binary_cross_entropy_with_logits(ra - fa.mean(), torch.full_like(ra, t_real))
+        B = F.binary_cross_entropy_with_logits(fa - ra.mean(), torch.full_like(fa, t_fake))
+        (0.3 * A + 0.7 * B).backward()
+        A2, B2 = ragan_bce_terms(rb, fb, t_real, t_fake)
+        (0.3 * A2 + 0.7 * B2).backward()
+        assert A2.item() == pytest.approx(A.item(), rel=1e-5, abs=1e-6) and B2.item() == pytest.approx(B.item(), rel=1e-5, abs=1e-6)
+        assert torch.allclose(rb.grad, ra.grad, rtol=1e-4, atol=1e-7) and torch.allclose(fb.grad, fa.grad, rtol=1e-4, atol=1e-7)
+
+
+def test_l1_loss_matches_torch(cuda_dev):
+    g = torch.Generator().manual_seed(4)
+    a0, b = torch.rand(2, 3, 64, 68, generator=g), torch.rand(2, 3, 64, 68, generator=g).to(cuda_dev)
+    a0[0, 0, 0, :8] = b[0, 0, 0, :8].cpu()   # exact ties: sign(0) = 0 like torch
+    a, a2 = a0.clone().to(cuda_dev).requires_grad_(True), a0.clone().to(cuda_dev).requires_grad_(True)
+    (1e-2 * F.l1_loss(a, b)).backward()
+    l2 = l1_loss(a2, b)
+    (1e-2 * l2).backward()
+    assert l2.item() == pytest.approx(F.l1_loss(a, b).item(), rel=1e-5)
+    assert torch.equal(a2.grad, a.grad)
+
+
+def test_gan_step_native_solver_matches_torch_solver(cuda_dev):
+    """The same GAN step (same native forward / backward kernels) with the native solver arithmetic and with torch's Adam /
+    BCE / L1: losses agree, and after two steps every parameter element agrees to Adam's own rounding — which also pins
+    the update itself element by element (the first step moves every element by lr * g / (|g| + eps))."""
+    def build(native):
+        netG = E.RRDBNet(3, 3, 32, 1)
+        netG.load_state_dict(O.synth_state_dict_g(3, 3, 32, 1, seed=61), strict=True)
+        netD = E.Discriminator_VGG_128(3, 64)
+        netD.load_state_dict(O.synth_state_dict_d(3, 64, seed=62), strict=True)
+        netG, netD = netG.to(cuda_dev).eval(), netD.to(cuda_dev).train()   # eval: GaussianNoise off -> comparable runs
+        return netG, netD, GanTrainStep(netG, netD, native_solver=native, lr_steps=[1], lr_gamma=0.5)
+    g = torch.Generator().manual_seed(9)
+    lr_img, hr_img = torch.rand(2, 3, 32, 32, generator=g).to(cuda_dev), torch.rand(2, 3, 128, 128, generator=g).to(cuda_dev)
+    Ga, Da, sa = build(True)
+    Gb, Db, sb = build(False)
+    p0 = {k: v.detach().clone() for k, v in Ga.named_parameters()}
+    for it in range(2):
+        la, lb = sa.step(lr_img, hr_img), sb.step(lr_img, hr_img)
+        for k in la:
+            assert la[k].item() == pytest.approx(lb[k].item(), rel=2e-3 if it else 2e-4, abs=1e-6), (it, k)
+        if it == 0:   # Adam's first step: |delta| = lr * |g| / (|g| + eps) -> lr wherever the gradient is not tiny
+            for k, p in Ga.named_parameters():
+                gr = p.grad
+                moved = (p.detach() - p0[k]).abs()
+                big = gr.abs() > 1e-6
+                assert torch.allclose(moved[big], torch.full_like(moved[big], 1e-4), rtol=2e-2), k
+                assert ((p.detach() - p0[k])[big].sign() == -gr[big].sign()).all(), k
+    assert sa.optimizer_G.param_groups[0]["lr"] == pytest.approx(5e-5)   # MultiStepLR halved it after step 1
+    for (k, p), (_, q) in list(zip(Ga.named_parameters(), Gb.named_parameters())) + list(zip(Da.named_parameters(), Db.named_parameters())):
+        # (elements whose gradient is rounding noise around zero may move the other way: at most 2 lr per step, and rare)
+        d = (p.detach() - q.detach()).abs()
+        assert d.max().item() <= 4.1e-4 and (d > 3e-6).float().mean().item() <= 2e-3, (k, d.max().item(), (d > 3e-6).float().mean().item())

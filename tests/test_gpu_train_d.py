@@ -114,6 +114,36 @@ def test_discriminator_backward_matches_oracle_autograd(cuda_dev):
     _check(d, y, dx, _ref(x, sd, r, True, True), "D train vs bf16-storage oracle", 0.2, 0.985)
 
 
+def test_discriminator_input_gradient_matches_reference_fixture(cuda_dev, golden_dir):
+    """dvgg128.npz: the gradient of sum(D(x)) w.r.t. the image that the REFERENCE's Discriminator_VGG_128 produced in
+    train mode (fp32).  Ten bf16 layers with BatchNorm over a batch of 4 make this the most sign-sensitive quantity of
+    the path; the stated bf16 bound is the one of the fp32-oracle test above."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(golden_dir, "dvgg128.npz"))
+    sd = O.synth_state_dict_d(3, 64, seed=41)
+    x = torch.from_numpy(g["x"])
+    d, y, dx = _run(cuda_dev, sd, x, torch.ones(4, 1), training=True)
+    ref_y = torch.from_numpy(g["y_train"])
+    assert (y - ref_y).abs().max().item() <= 5e-2 * max(1.0, ref_y.abs().max().item())
+    rel, cos = _rel(dx, torch.from_numpy(g["gx_train"]))
+    print(f"D input gradient vs reference fixture: rel_l2 {rel:.3e} cos {cos:.5f}")
+    assert rel <= 0.3 and cos >= 0.95, (rel, cos)   # measured 0.198 / 0.980
+
+
+def test_discriminator_frozen_input_gradient_vs_fp32_oracle(cuda_dev):
+    """G phase (SRRaGAN_model.py:115-116,140) against the fp32 oracle (not only its bf16-storage emulation)."""
+    sd = O.synth_state_dict_d(3, 64, seed=43)
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(2, 3, 128, 128, generator=g)
+    r = torch.randn(2, 1, generator=g)
+    d, y, dx = _run(cuda_dev, sd, x, r, training=True, frozen=True)
+    ry, rdx, _ = _ref(x, sd, r, True, False)
+    rel, cos = _rel(dx, rdx)
+    print(f"D frozen input gradient vs fp32 oracle: rel_l2 {rel:.3e} cos {cos:.5f}")
+    assert rel <= 0.35 and cos >= 0.94, (rel, cos)   # measured 0.221 / 0.975
+
+
 def test_discriminator_backward_frozen_gives_input_gradient_only(cuda_dev):
     """G phase (SRRaGAN_model.py:115-116,140): D parameters frozen, the gradient flows to the image."""
     sd = O.synth_state_dict_d(3, 64, seed=43)

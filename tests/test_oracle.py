@@ -100,6 +100,25 @@ def test_discriminator(golden_dir):
             _close(v, ref, tol=1e-5)
 
 
+def test_oracle_gradients_match_reference_fixture(golden_dir):
+    """The oracle differentiated by torch autograd reproduces the gradients the REFERENCE's RRDBNet produced
+    (tests/golden/make_golden_grads.py): the gradient parity tests on the GPU stand on this."""
+    g = _load(golden_dir, "rrdbnet_grad_nb1_nf64.npz")
+    sd = {k: v.clone().requires_grad_(True) for k, v in O.synth_state_dict_g(3, 3, 64, 1, seed=11).items()}
+    y = O.rrdbnet_forward(torch.from_numpy(g["x"]), sd, nb=1)
+    _close(y.detach(), g["y"], tol=1e-5)
+    (y * torch.from_numpy(g["gy"])).sum().backward()
+    for k in [str(n) for n in g["names"]]:
+        gr = sd[k].grad
+        ref = g["norm." + k]
+        assert abs(gr.norm().item() - ref[0]) <= 1e-4 * ref[0] + 1e-9, k
+        assert abs(gr.abs().max().item() - ref[2]) <= 1e-3 * ref[2] + 1e-9, k
+        head = torch.from_numpy(g["head." + k])
+        assert (gr.flatten()[:64] - head).abs().max().item() <= 1e-3 * max(ref[2], 1e-12), k
+        if "full." + k in g:
+            _close(gr, g["full." + k], tol=1e-3)
+
+
 def test_golden_meta(golden_dir):
     meta = json.load(open(os.path.join(golden_dir, "meta.json")))
     assert meta["test_image_RRDB_Net_equals_RRDBNet_eval"] and meta["test_image_keys_equal"]

@@ -71,3 +71,30 @@ def test_world2_gloo_shards_and_gathers():
         assert p.exitcode == 0
     assert all(ok for ok, _ in res)
     assert sorted(n for _, n in res) == [3, 3]  # 6 crops of 32x32, 3 per rank
+
+
+def test_halo_makes_the_interior_converge_to_the_whole_image_forward():
+    """crops with zero padding at every crop edge leave seams.  With a stand-in network of receptive radius 3
+    (three 3x3 convs, zero padding, then nearest x4) a halo >= 3 reproduces the whole-image forward EXACTLY everywhere;
+    halo = 0 differs along the crop borders only; image borders are zero-padded in both (like the reference's forward)."""
+    torch.manual_seed(0)
+    w1, w2, w3 = (torch.randn(3, 3, 3, 3) * 0.3 for _ in range(3))
+
+    def net(x):
+        for wt in (w1, w2, w3):
+            x = F.leaky_relu(F.conv2d(x, wt, padding=1), 0.2)
+        return F.interpolate(x, scale_factor=4, mode="nearest")
+
+    img = torch.rand(1, 3, 40, 56)
+    whole = net(img)
+    seams = tiled.infer_tiled(net, img, 16, halo=0)
+    exact = tiled.infer_tiled(net, img, 16, halo=3)
+    assert torch.allclose(exact, whole, atol=1e-6), (exact - whole).abs().max()
+    assert torch.allclose(tiled.infer_tiled(net, img, 16, halo=8), whole, atol=1e-6)
+    d = (seams - whole).abs().amax(dim=(0, 1))
+    assert d.max() > 1e-3, "halo = 0 must show the seam this test is about"
+    interior = d[4 * 4:4 * 12, 4 * 4:4 * 12]      # centre of the first crop, more than 3 LR pixels from its edges
+    assert interior.max() < 1e-6
+    # read regions never leave the image and keep the crop at the stated offset
+    assert tiled.with_halo((0, 16, 16, 16), 40, 56, 3) == (0, 13, 19, 22, 0, 3)
+    assert tiled.with_halo((32, 48, 8, 8), 40, 56, 3) == (29, 45, 11, 11, 3, 3)
