@@ -29,13 +29,53 @@ def _flat(*groups) -> nn.Sequential:
     return nn.Sequential(*mods)
 
 
+_LIVE_MODULES = None      # weakref.WeakSet of constructed native modules
+_OPT_MODULES = {}         # id(optimizer) -> (weakref to the optimizer, [weakrefs to the native modules it updates])
+
+
+def _after_optimizer_step(optimizer, args, kwargs):
+    """Global ``torch.optim`` post-step hook: whatever optimizer just updated parameters of a native module, the module's
+    derived weight cache is stale.  Needed because not every optimizer moves the tensors' version counters —
+    ``torch.optim.Adam(fused=True)`` updates through ``torch._fused_adam_`` and leaves ``_version`` untouched (torch 2.11),
+    so round 1's version-only check silently kept running the first step's weights."""
+    import weakref
+    ent = _OPT_MODULES.get(id(optimizer))
+    if ent is None or ent[0]() is not optimizer:
+        ids = {id(p) for g in optimizer.param_groups for p in g["params"]}
+        mods = [weakref.ref(m) for m in list(_LIVE_MODULES or ()) if any(id(p) in ids for p in m.parameters())]
+        try:
+            ent = (weakref.ref(optimizer), mods)
+        except TypeError:
+            ent = (lambda: None, mods)
+        if len(_OPT_MODULES) > 64:
+            _OPT_MODULES.clear()
+        _OPT_MODULES[id(optimizer)] = ent
+    for r in ent[1]:
+        m = r()
+        if m is not None:
+            m.invalidate_weights()
+
+
+def _register_native_module(module) -> None:
+    global _LIVE_MODULES
+    import weakref
+    if _LIVE_MODULES is None:
+        _LIVE_MODULES = weakref.WeakSet()
+        from torch.optim.optimizer import register_optimizer_step_post_hook
+        register_optimizer_step_post_hook(_after_optimizer_step)
+    _LIVE_MODULES.add(module)
+    _OPT_MODULES.clear()   # (an optimizer seen before may cover this module as well)
+
+
 class _NativeWeights:
     """Mixin of the top-level classes: the native engines keep DERIVED bf16 weight tiles and repack them when a
     Parameter's storage pointer or in-place version counter changes.  Writes through ``.data`` bump no version
     counter (``m.weight.data *= scale`` / ``init.kaiming_normal_(m.weight.data)`` in the reference's ``init_weights``,
     networks.py:30-44, run via ``net.apply(fn)``), so every bulk entry point that may hide such writes bumps an
-    epoch the engines compare as well: ``apply``, ``_apply`` (``.to()`` / ``.cuda()``), ``load_state_dict``.  After any
-    other ``.data`` write (EMA, weight interpolation, clipping) call ``invalidate_weights()``."""
+    epoch the engines compare as well: ``apply``, ``_apply`` (``.to()`` / ``.cuda()``), ``load_state_dict``, and every
+    ``torch.optim`` optimizer step that covers one of the module's parameters (a global post-step hook:
+    ``Adam(fused=True)`` bumps no version counter either).  After any other ``.data`` write (EMA, weight interpolation,
+    clipping) call ``invalidate_weights()``."""
 
     def invalidate_weights(self) -> None:
         object.__setattr__(self, "_esrp_epoch", self.__dict__.get("_esrp_epoch", 0) + 1)
@@ -88,6 +128,7 @@ class _GeneratorBase(_NativeWeights, nn.Module):
         # native engines, one per device; kept out of the module/state machinery on purpose
         object.__setattr__(self, "_engines", {})
         object.__setattr__(self, "_step", 0)
+        _register_native_module(self)
 
     # -- engine plumbing -----------------------------------------------------------------------
     def __getstate__(self):
@@ -137,7 +178,11 @@ class _GeneratorBase(_NativeWeights, nn.Module):
                                "(use the reference modules for CPU inference)")
         from .discriminator import _named_params
         names, plist = _named_params(self)
-        params: Dict[str, torch.Tensor] = dict(zip(names, plist))
+        params = self.__dict__.get("_esrp_params_dict")
+        if params is None or params[0] is not plist:
+            params = (plist, dict(zip(names, plist)))
+            object.__setattr__(self, "_esrp_params_dict", params)
+        params = params[1]
         needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in plist))
         if needs_grad:
             from .autograd import generator_apply
@@ -190,6 +235,7 @@ class Discriminator_VGG_128(_NativeWeights, nn.Module):
                                 for ci, co, k, s, nt in plan])
         self.classifier = nn.Sequential(nn.Linear(512 * 4 * 4, 100), nn.LeakyReLU(0.2, True), nn.Linear(100, 1))
         object.__setattr__(self, "_engines", {})
+        _register_native_module(self)
 
     def __getstate__(self):
         st = self.__dict__.copy()

@@ -16,6 +16,12 @@ def _stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# When a list is installed here, the weight-pack wrappers below append the raw C-ABI call they make as
+# (function, arguments without the trailing stream, keep-alive objects): a caller that repacks the same tensors after every
+# optimizer step (the discriminator engine) replays those calls instead of re-deriving them in Python (~55 us each).
+RECORD: Optional[list] = None
+
+
 def _i32_array(vals: Sequence[int]):
     arr = (C.c_int32 * len(vals))(*vals)
     return arr
@@ -44,10 +50,12 @@ def pack_conv3x3_weights(w_oihw: torch.Tensor, kc: int, bn: int, chunk_lc0: Sequ
     if out is None:
         out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
     assert out.numel() == nbytes and out.dtype == torch.uint8   # `out=`: repack in place (cached descriptors keep their pointer)
-    _lib.check(lib.esrp_pack_conv3x3_weights(w.data_ptr(), w_o, w_i, int(transpose), layout, row0, rows, kc, bn,
-                                             len(chunk_lc0), _i32_array(chunk_lc0), aux_ptr, aux_cin, aux_chunks,
-                                             out.data_ptr(), _stream_ptr()),
-               "esrp_pack_conv3x3_weights")
+    lc0 = _i32_array(chunk_lc0)
+    args = (w.data_ptr(), w_o, w_i, int(transpose), layout, row0, rows, kc, bn, len(chunk_lc0), lc0, aux_ptr, aux_cin, aux_chunks,
+            out.data_ptr())
+    _lib.check(lib.esrp_pack_conv3x3_weights(*args, _stream_ptr()), "esrp_pack_conv3x3_weights")
+    if RECORD is not None:
+        RECORD.append((lib.esrp_pack_conv3x3_weights, args, (w, w_aux, out, lc0)))
     return out
 
 
@@ -224,8 +232,10 @@ def pack_dgrad_weights(groups: Sequence[Optional[tuple]], row0: int, rows: int, 
     chunks = (len(groups) * 32 + kc - 1) // kc
     if out is None:
         out = torch.empty(lib.esrp_packed_conv3x3_bytes(chunks, kc, bn, 0), dtype=torch.uint8, device=dev)
-    _lib.check(lib.esrp_pack_dgrad_weights(arr, len(groups), layout, row0, rows, kc, bn, out.data_ptr(), _stream_ptr()),
-               "esrp_pack_dgrad_weights")
+    args = (arr, len(groups), layout, row0, rows, kc, bn, out.data_ptr())
+    _lib.check(lib.esrp_pack_dgrad_weights(*args, _stream_ptr()), "esrp_pack_dgrad_weights")
+    if RECORD is not None:
+        RECORD.append((lib.esrp_pack_dgrad_weights, args, (keep, out, arr)))
     return out
 
 

@@ -96,7 +96,7 @@ class _Layer:
         self.packed: Dict[Tuple[int, int, int], torch.Tensor] = {}   # (layout, slice, kgroup) -> packed weights
         self.packed_t: Dict[Tuple[int, int], torch.Tensor] = {}      # (layout, input-channel slice) -> dgrad weights
         self.wg_tab = None                                           # cached wgrad unit / scatter tables
-        self.repack: List = []                                       # closures that rebuild every packed tile in place
+        self.repack: List = []                                       # recorded C-ABI calls (fn, args, keep-alive) that rebuild every packed tile in place
         self.bias_pad: Optional[torch.Tensor] = None
         self.w3: Optional[torch.Tensor] = None
         self.sig = None
@@ -269,18 +269,23 @@ class DiscriminatorEngine:
                 _rearrange_k4s2(w.detach(), out=L.w3)
             if b is not None:
                 L.bias_pad.copy_(b.detach())
-        for fn in L.repack:
-            fn()
+        st = _stream()
+        for fn, args, _keep in L.repack:   # raw C-ABI calls recorded when each packed tensor was first built
+            rc = fn(*args, st)
+            if rc != 0:
+                _lib.check(rc, "weight repack")
         L.sig = sig
 
     def _packed(self, L: _Layer, layout: int, s: int, g: int, chunks: List[int], sl: int = SLICE) -> torch.Tensor:
         key = (layout, s, g, sl)
         t = L.packed.get(key)
         if t is None:
-            t = K.pack_conv3x3_weights(L.w3, L.kc, sl, chunks, row0=s * sl, rows=sl, layout=layout)
+            K.RECORD = L.repack   # the call that builds the tile is the call that rebuilds it (same source / destination pointers)
+            try:
+                t = K.pack_conv3x3_weights(L.w3, L.kc, sl, chunks, row0=s * sl, rows=sl, layout=layout)
+            finally:
+                K.RECORD = None
             L.packed[key] = t
-            L.repack.append(lambda t=t, chunks=list(chunks): K.pack_conv3x3_weights(
-                L.w3, L.kc, sl, chunks, row0=s * sl, rows=sl, layout=layout, out=t))
         return t
 
     def _fan_out(self, launches: int, pixels: int) -> bool:
@@ -442,10 +447,12 @@ class DiscriminatorEngine:
         t = L.packed_t.get(key)
         if t is None:
             groups = [(L.w3, 32 * g, 1.0) for g in range(L.cout // 32)]
-            t = K.pack_dgrad_weights(groups, s * sl, min(sl, L.cin_eff - s * sl), kc, sl, layout=layout)
+            K.RECORD = L.repack
+            try:
+                t = K.pack_dgrad_weights(groups, s * sl, min(sl, L.cin_eff - s * sl), kc, sl, layout=layout)
+            finally:
+                K.RECORD = None
             L.packed_t[key] = t
-            L.repack.append(lambda t=t, groups=groups: K.pack_dgrad_weights(
-                groups, s * sl, min(sl, L.cin_eff - s * sl), kc, sl, layout=layout, out=t))
         return t
 
     def _wgrad_tables(self, L: _Layer):
@@ -521,9 +528,12 @@ class DiscriminatorEngine:
             wp = L.packed_t.get((layout, -1, 16))
             if wp is None:
                 groups = [(L.w3, 32 * g, 1.0) for g in range(L.cout // 32)]
-                wp = K.pack_dgrad_weights(groups, 0, L.cin, kc, 16, layout=layout)
+                K.RECORD = L.repack
+                try:
+                    wp = K.pack_dgrad_weights(groups, 0, L.cin, kc, 16, layout=layout)
+                finally:
+                    K.RECORD = None
                 L.packed_t[(layout, -1, 16)] = wp
-                L.repack.append(lambda wp=wp, groups=groups: K.pack_dgrad_weights(groups, 0, L.cin, kc, 16, layout=layout, out=wp))
             d = self._t(K.ConvCall(n=n, h=gh, w=gw, srcs=[dz], kc=kc, chunks=chunks, bn=16, cout=L.cin, w_packed=wp, w_layout=layout,
                                    out_nchw=out_nchw).desc())
             self._c(self.lib.esrp_conv3x3_nhwc, "esrp_conv3x3_nhwc", C.byref(d), st)

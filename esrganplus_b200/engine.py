@@ -46,15 +46,21 @@ class GeneratorEngine:
         """Repack if any source tensor changed. `named_params`: state_dict-style key -> fp32 tensor
         on this device; `epoch`: the module's invalidation counter (writes through ``.data`` bump no tensor
         version, see architecture._NativeWeights). Returns True when a repack was launched."""
-        tensors = []
-        for k in self.keys:
-            t = named_params.get(k)
-            if t is None:
-                raise RuntimeError(f"RRDBNet engine: parameter {k!r} missing from the module")
-            if t.device != self.device or t.dtype != torch.float32:
-                raise RuntimeError(f"RRDBNet engine: {k} must be fp32 on {self.device}, got {t.dtype} on {t.device}")
-            tensors.append(t if t.is_contiguous() else t.contiguous())
-        sig = (epoch, tuple((t.data_ptr(), t._version) for t in tensors))
+        cached = getattr(self, "_param_cache", None)
+        if cached is not None and cached[0] is named_params:
+            tensors = cached[1]   # same dict object as last time (callers cache it per module): the tensors were validated then
+        else:
+            tensors = []
+            for k in self.keys:
+                t = named_params.get(k)
+                if t is None:
+                    raise RuntimeError(f"RRDBNet engine: parameter {k!r} missing from the module")
+                if t.device != self.device or t.dtype != torch.float32:
+                    raise RuntimeError(f"RRDBNet engine: {k} must be fp32 on {self.device}, got {t.dtype} on {t.device}")
+                tensors.append(t if t.is_contiguous() else t.contiguous())
+            if all(t is named_params[k] for t, k in zip(tensors, self.keys)):   # (a contiguous() copy must be re-made every time)
+                self._param_cache = (named_params, tensors)
+        sig = (epoch, tuple([(t.data_ptr(), t._version) for t in tensors]))
         if sig == self._sig:
             return False
         ptrs = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
@@ -241,6 +247,33 @@ class GeneratorEngine:
             else:
                 grads.append(part[:numel].view(shp))
         return grads, flat
+
+    def backward_flat(self, dy: torch.Tensor, token: int):
+        """Like `backward` with every tensor needed, but into a PERSISTENT flat buffer whose per-tensor views are created
+        once (`grad_views`): no per-step allocation, split or view creation for the 771 tensors.  Returns the flat buffer."""
+        import numpy as np
+        if token != getattr(self, "_train_token", None):
+            raise RuntimeError("RRDBNet backward: the saved activations of this forward were overwritten by a later "
+                               "training forward of the same module (one forward/backward pair at a time)")
+        if dy.dtype != torch.float32 or dy.device != self.device:
+            raise RuntimeError("RRDBNet backward expects an fp32 gradient on the module's device")
+        dy = dy.contiguous()
+        if getattr(self, "_flat_grad", None) is None:
+            shapes, offs, total = self._grad_layout()
+            self._flat_grad = torch.zeros(total, dtype=torch.float32, device=self.device)
+            ptrs = np.ascontiguousarray(offs * np.uint64(4) + np.uint64(self._flat_grad.data_ptr()))
+            self._flat_ptrs = ptrs
+            sizes, numels = self._grad_split_sizes()
+            self.grad_views = [part[:n].view(shp) if part.numel() != n else part.view(shp)
+                               for part, shp, n in zip(self._flat_grad.split(sizes), shapes, numels)]
+        ws, aligned = self._train_ws
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.esrp_rrdbnet_backward(self.handle, dy.data_ptr(),
+                                                      self._flat_ptrs.ctypes.data_as(C.POINTER(C.c_void_p)), len(self.grad_views), aligned,
+                                                      torch.cuda.current_stream(self.device).cuda_stream),
+                       "esrp_rrdbnet_backward")
+        self._train_token += 1  # consumed
+        return self._flat_grad
 
     def _grad_split_sizes(self):
         c = getattr(self, "_gsplit", None)

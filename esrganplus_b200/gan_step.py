@@ -28,7 +28,9 @@ class GanTrainStep:
         self.native = on_cuda if native_solver is None else bool(native_solver)
         pg = [p for p in netG.parameters() if p.requires_grad]
         if self.native:
+            from .autograd import enable_flat_grads
             from .solver import FlatAdam
+            enable_flat_grads(netG)   # the backward points p.grad at slices of one persistent flat buffer (autograd.py)
             # SRRaGAN_model.py:77-89 as one kernel per network over flat storage
             self.optimizer_G = FlatAdam(pg, lr=lr_G, weight_decay=weight_decay_G, betas=(beta1_G, 0.999), module=netG)
             self.optimizer_D = FlatAdam(list(netD.parameters()), lr=lr_D, weight_decay=weight_decay_D, betas=(beta1_D, 0.999),

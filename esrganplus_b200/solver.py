@@ -63,6 +63,9 @@ class FlatAdam(torch.optim.Optimizer):
                              "exp_avg_sq": self._flat_v[o:o + n].view(p.shape)}
 
     def _rehome(self) -> None:
+        base = self._flat_p.data_ptr()
+        if all(p.data_ptr() == base + o * 4 for p, o in zip(self._plist, self._offs)):
+            return   # (the common case, ~0.1 ms for 771 tensors)
         with torch.no_grad():
             for p, o in zip(self._plist, self._offs):
                 n = p.numel()

@@ -197,3 +197,22 @@ def test_conv_descriptor_validation_of_optional_fields():
     assert "k_valid" in err(desc(k_valid=-1))
     assert "k_valid" in err(desc(num_chunks=2, k_valid=64, src_ctotal=(ctypes.c_int32 * 2)(128, 0),
                                  chunk_c0=(ctypes.c_int32 * _lib.ESRP_MAX_CHUNKS)(0, 64)))
+
+
+def test_optimizer_steps_invalidate_the_derived_weight_cache():
+    """torch.optim.Adam(fused=True) updates parameters without moving their version counters (torch 2.11): the engines'
+    (pointer, version) signature cannot see it, the modules' invalidation epoch must (architecture._after_optimizer_step)."""
+    import torch
+    import esrganplus_b200 as E
+    g = E.RRDBNet(3, 3, 32, 1)
+    d = E.Discriminator_VGG_128(3, 64)
+    for p in list(g.parameters()) + list(d.parameters()):
+        p.grad = torch.zeros_like(p)
+    for kw in ({"fused": True}, {}):
+        opt_g = torch.optim.Adam(g.parameters(), lr=1e-4, **kw)
+        e_g, e_d = g.weights_epoch, d.weights_epoch
+        opt_g.step()
+        assert g.weights_epoch > e_g and d.weights_epoch == e_d, kw
+        opt_d = torch.optim.SGD(d.parameters(), lr=0.1)
+        opt_d.step()
+        assert d.weights_epoch > e_d
