@@ -323,6 +323,10 @@ class DiscriminatorEngine:
         out_b = self._t(torch.empty((n, gh, gw, L.cout), dtype=torch.bfloat16, device=self.device)) if fused else None
         SLICE = self._slice_width(L.cout, layout, max(len(g_) for g_ in groups))
         fan = self._fan_out(L.cout // SLICE, n * gh * gw)
+        # every weight tile exists BEFORE the fork: a tile built lazily inside the fan-out region is packed on the main
+        # stream after the side streams have branched off, i.e. unordered with the launch that reads it
+        tiles = [[self._packed(L, layout, s, g, [ch * L.kc for ch in chs], SLICE) for g, chs in enumerate(groups)]
+                 for s in range(L.cout // SLICE)]
         if fan:
             self._c(self.lib.esrp_streams_fork, "esrp_streams_fork", st, self.side, self.nside)
         main_st = st
@@ -332,7 +336,7 @@ class DiscriminatorEngine:
                 last = g == len(groups) - 1
                 lc0 = [ch * L.kc for ch in chs]
                 call = K.ConvCall(n=n, h=gh, w=gw, srcs=[src], kc=L.kc, chunks=[(0, c0) for c0 in lc0], bn=SLICE,
-                                  cout=SLICE, w_packed=self._packed(L, layout, s, g, lc0, SLICE), w_layout=layout,
+                                  cout=SLICE, w_packed=tiles[s][g], w_layout=layout,
                                   bias=L.bias_pad[s * SLICE:(s + 1) * SLICE] if last else None,
                                   act=1 if fused else 0)
                 if fused:
@@ -541,11 +545,12 @@ class DiscriminatorEngine:
         out = self._t(torch.empty((n, gh, gw, L.cin_eff), dtype=torch.bfloat16, device=self.device))
         SLICE = self._slice_width(L.cin_eff, layout, nchunks)
         fan = self._fan_out(L.cin_eff // SLICE, n * gh * gw)
+        tiles = [self._dgrad_packed(L, layout, s, kc, SLICE) for s in range(L.cin_eff // SLICE)]   # before the fork (see _conv)
         if fan:
             self._c(self.lib.esrp_streams_fork, "esrp_streams_fork", st, self.side, self.nside)
         for s in range(L.cin_eff // SLICE):
             d = self._t(K.ConvCall(n=n, h=gh, w=gw, srcs=[dz], kc=kc, chunks=chunks, bn=SLICE, cout=SLICE,
-                                   w_packed=self._dgrad_packed(L, layout, s, kc, SLICE), w_layout=layout, out_bf16=out,
+                                   w_packed=tiles[s], w_layout=layout, out_bf16=out,
                                    ob_c0=s * SLICE).desc())
             self._c(self.lib.esrp_conv3x3_nhwc, "esrp_conv3x3_nhwc", C.byref(d), self.side[s % self.nside] if fan else st)
         if fan:

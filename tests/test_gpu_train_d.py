@@ -194,3 +194,35 @@ def test_discriminator_eval_mode_backward(cuda_dev):
     for k in ("features.27.weight", "features.27.bias", "features.26.weight", "features.26.bias", "classifier.0.weight"):
         rel, cos = _rel(dict(d.named_parameters())[k].grad, rg[k])
         assert rel <= 0.12 and cos >= 0.99, (k, rel, cos)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [3, 6])
+def test_first_pass_of_a_new_discriminator_reads_no_unwritten_memory(cuda_dev, n):
+    """The first pass of a shape builds the packed weight tiles lazily while it records its launch plan; the deep layers
+    fan their output slices out to side streams.  A tile packed after the fork is unordered with the launch that reads
+    it: with a fresh process's zeroed pages that went unnoticed, with recycled memory (a second model in one process:
+    bench.py's weak + strong training legs) the first logits were NaN.  Prime the allocator with NaN blocks, then the
+    recording pass must equal the replayed ones (up to the summation order of the BatchNorm statistics), forward and input
+    gradient."""
+    from esrganplus_b200.synth import random_state_dict_d
+    blocks = [torch.full((sz // 4,), float("nan"), device=cuda_dev)
+              for sz in [1 << 28] * 8 + [1 << 24] * 16 + [1 << 20] * 64 + [1 << 16] * 128 + [1 << 12] * 256 + [512] * 1024]
+    torch.cuda.synchronize()
+    del blocks
+    d = E.Discriminator_VGG_128(3, 64)
+    d.load_state_dict(random_state_dict_d(3, 64, seed=77), strict=True)
+    d = d.to(cuda_dev).train()
+    for p in d.parameters():
+        p.requires_grad = False
+    x = torch.rand(n, 3, 128, 128, generator=torch.Generator().manual_seed(n)).to(cuda_dev)
+    outs = []
+    for _ in range(3):
+        xi = x.clone().requires_grad_(True)
+        y = d(xi)
+        y.sum().backward()
+        outs.append((y.detach().clone(), xi.grad.clone()))
+    assert torch.isfinite(outs[0][0]).all() and torch.isfinite(outs[0][1]).all()
+    for y, dx in outs[1:]:
+        assert torch.allclose(y, outs[0][0], rtol=1e-4, atol=1e-5)
+        assert (dx - outs[0][1]).norm().item() <= 1e-3 * outs[0][1].norm().item()

@@ -1,4 +1,6 @@
 #!/bin/bash
-mkdir -p gpurun_out; : > gpurun_out/t_diag.jsonl
-for m in torch native; do timeout 120 python tools/diag_solver.py $m >> gpurun_out/t_diag.jsonl 2>> gpurun_out/t_err.log; done
-cat gpurun_out/t_diag.jsonl; tail -3 gpurun_out/t_err.log
+# 2-GPU check of the bench (flat-gradient all-reduce path) + strong-scaling train leg
+mkdir -p gpurun_out
+timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+  bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/t_bench2.json 2> gpurun_out/t_bench2.err
+echo "rc=$?"; tail -c 3000 gpurun_out/t_bench2.json; tail -5 gpurun_out/t_bench2.err
