@@ -452,6 +452,49 @@ def test_config2_full_size_properties(cuda_dev):
     _net_close(y1.cpu(), ref, "config 2 tile 3")
 
 
+@pytest.mark.parametrize("shape", [(2, 40, 72), (3, 24, 24)])
+def test_repeated_forwards_of_one_plan_are_consistent(cuda_dev, shape):
+    """A cached launch plan is reused by every later forward of its shape: with other input / output tensors, on another
+    stream, after a weight update (the plan holds pointers to the packed tiles, which are rebuilt in place), after a
+    detour through another shape — and inside a CUDA graph captured by the caller (tools/bench_fwd_graph.py measured
+    13.0 vs 13.15 ms for config 2: the launch stream is not what bounds the step, so the engine does not capture its
+    own)."""
+    sd = O.synth_state_dict_g(3, 3, 32, 2, seed=5)
+    net = _make(E.RRDBNet, sd, 32, 2, cuda_dev)
+    g = torch.Generator().manual_seed(1)
+    xa, xb = (torch.rand(*[shape[0], 3, shape[1], shape[2]], generator=g).to(cuda_dev) for _ in range(2))
+    ya = net(xa)
+    assert torch.equal(net(xa), ya)
+    yb = net(xb)
+    assert not torch.equal(yb, ya)
+    assert torch.equal(net(xa), ya)
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        ys = net(xb)
+    st.synchronize()
+    assert torch.equal(ys, yb)
+    _net_close(yb.cpu(), O.rrdbnet_forward(xb.cpu(), sd, 2), "repeated forward vs oracle")
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(0.5)
+    sd_half = {k: v * 0.5 for k, v in sd.items()}
+    _net_close(net(xb).cpu(), O.rrdbnet_forward(xb.cpu(), sd_half, 2), "forward after a weight update")
+    net(xa[:1])                       # a shape change rebuilds the plan
+    yh = net(xb)
+    assert torch.equal(net(xb), yh)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side), torch.no_grad():
+        net(xb)
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=side):
+            yg = net(xb)
+        gr.replay()
+    side.synchronize()
+    assert torch.equal(yg, yh)
+
+
 # ---------------------------------------------------------------------------------------------------
 # persistent conv chain (csrc/conv3x3_chain.cuh): the dense-block convs of the trunk as phases of ONE launch
 # ---------------------------------------------------------------------------------------------------
