@@ -4,6 +4,6 @@ Public surface = the reference's network classes (see architecture.py) over libe
 (C ABI in include/esrp.h).  Importing the package does not load the shared library; the first
 forward does, and raises if it is missing.
 """
-from .architecture import Discriminator_VGG_128, RRDB_Net, RRDBNet  # noqa: F401
+from .architecture import Discriminator_VGG_128, RRDB_Net, RRDBNet, VGGFeatureExtractor  # noqa: F401
 
-__all__ = ["RRDBNet", "RRDB_Net", "Discriminator_VGG_128"]
+__all__ = ["RRDBNet", "RRDB_Net", "Discriminator_VGG_128", "VGGFeatureExtractor"]

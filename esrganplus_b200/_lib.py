@@ -196,6 +196,12 @@ SYMBOLS = {
     "esrp_graph_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
     "esrp_graph_destroy": (None, [C.c_void_p]),
     "esrp_memset_zero": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
+    "esrp_nchw_f32_to_nhwc_bf16_affine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                                    C.c_int32, C.c_int32, C.c_void_p]),
+    "esrp_maxpool2x2_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "esrp_relu_bwd_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "esrp_maxpool2x2_relu_bwd_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                                     C.c_void_p]),
 }
 
 _lib = None

@@ -247,3 +247,69 @@ class Discriminator_VGG_128(_NativeWeights, nn.Module):
             raise RuntimeError("esrganplus_b200.Discriminator_VGG_128 runs on CUDA (sm_100a) only")
         from .discriminator import discriminator_apply
         return discriminator_apply(self, x)
+
+
+# torchvision.models.vgg19 configuration 'E' (architecture.py:289): out-channels per conv, 'M' = MaxPool2d(2, 2)
+_VGG19_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512, 512, 512, 512, "M"]
+
+
+class VGGFeatureExtractor(_NativeWeights, nn.Module):
+    """architecture.py:279-307: `(x - mean) / std`, then torchvision's vgg19().features[:feature_layer + 1] with frozen
+    weights (feature_layer = 34: conv5_4 before its ReLU, networks.py:144-155).  Same constructor arguments, module tree
+    (`features` = Sequential of Conv2d / ReLU(inplace) / MaxPool2d at torchvision's indices), buffers (`mean`, `std`) and
+    state_dict keys as the reference, so `networks.define_F` builds it unchanged and a torchvision vgg19 checkpoint loads
+    through `load_vgg19_state_dict`.
+
+    One difference is unavoidable offline: the reference constructor downloads the pretrained torchvision weights
+    (`pretrained=True`, :289).  This class does that only when `pretrained=True` is passed AND torchvision can supply
+    them; by default the convs are torchvision-initialised (kaiming normal) and the caller loads weights.
+    `use_bn=True` (vgg19_bn, feature_layer 49) is not on the ESRGAN+ path (networks.py:58 passes use_bn=False)."""
+
+    def __init__(self, feature_layer=34, use_bn=False, use_input_norm=True, device=torch.device("cpu"), pretrained=False):
+        super().__init__()
+        if use_bn:
+            raise NotImplementedError("VGGFeatureExtractor: use_bn=True (vgg19_bn) is not on the ESRGAN+ path")
+        self.use_input_norm = use_input_norm
+        if self.use_input_norm:
+            self.register_buffer("mean", torch.Tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1).to(device))
+            self.register_buffer("std", torch.Tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1).to(device))
+        layers, cin = [], 3
+        for v in _VGG19_CFG:
+            if v == "M":
+                layers.append(nn.MaxPool2d(kernel_size=2, stride=2))
+            else:
+                conv = nn.Conv2d(cin, v, kernel_size=3, padding=1)
+                nn.init.kaiming_normal_(conv.weight, mode="fan_out", nonlinearity="relu")   # torchvision/models/vgg.py
+                nn.init.constant_(conv.bias, 0)
+                layers += [conv, nn.ReLU(inplace=True)]
+                cin = v
+        self.features = nn.Sequential(*layers[:feature_layer + 1])
+        if not isinstance(self.features[-1], nn.Conv2d):
+            raise NotImplementedError("VGGFeatureExtractor: feature_layer must index a conv (features before the ReLU)")
+        if pretrained:
+            import torchvision
+            self.load_vgg19_state_dict(torchvision.models.vgg19(weights="IMAGENET1K_V1").state_dict())
+        for _k, v in self.features.named_parameters():   # "No need to BP to variable" (:299-301)
+            v.requires_grad = False
+        object.__setattr__(self, "_engines", {})
+        _register_native_module(self)
+
+    def load_vgg19_state_dict(self, sd):
+        """Load a torchvision vgg19 state_dict (`features.N.*` + `classifier.*`): the keys of the kept layers are identical."""
+        own = self.state_dict()
+        picked = {k: v for k, v in sd.items() if k in own}
+        missing = [k for k in own if k.startswith("features.") and k not in picked]
+        if missing:
+            raise KeyError(f"load_vgg19_state_dict: missing {missing[:4]}...")
+        self.load_state_dict({**own, **picked}, strict=True)
+
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st["_engines"] = {}
+        return st
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError("esrganplus_b200.VGGFeatureExtractor runs on CUDA (sm_100a) only")
+        from .vgg_feature import feature_apply
+        return feature_apply(self, x)

@@ -522,8 +522,9 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
             if (store) ext_mask_store<GC>(p, pix, gch, v);
           }
           if (p.act) {
+            const float slope = p.act == 2 ? 0.f : 0.2f;  // LeakyReLU(0.2) / ReLU
 #pragma unroll
-            for (int i = 0; i < GC; ++i) v[i] = fmaxf(v[i], 0.2f * v[i]);  // LeakyReLU(0.2)
+            for (int i = 0; i < GC; ++i) v[i] = fmaxf(v[i], slope * v[i]);
           }
           if (p.s0 != 1.0f) {
 #pragma unroll

@@ -402,8 +402,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
           for (int i = 0; i < GC; ++i) v[i] += bias_s[ch0 + i];
           if constexpr (EXT) ext_mask_store<GC>(p, pix, ch0, v);
           if (p.act) {
+            const float slope = p.act == 2 ? 0.f : 0.2f;  // LeakyReLU(0.2) / ReLU
 #pragma unroll
-            for (int i = 0; i < GC; ++i) v[i] = lrelu02(v[i]);
+            for (int i = 0; i < GC; ++i) v[i] = fmaxf(v[i], slope * v[i]);
           }
           if (p.s0 != 1.0f) {
 #pragma unroll

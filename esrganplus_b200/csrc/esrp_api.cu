@@ -139,6 +139,7 @@ int plan_conv(const esrp_conv3x3_t& d, ConvLaunch* out) {
   if (d.aux_chunks < 0 || d.aux_chunks > d.num_chunks) return set_error("conv3x3: aux_chunks=%d out of range", d.aux_chunks);
   if (!d.src[0] || !d.w_packed) return set_error("conv3x3: null src/weights");
   if (d.cout < 1 || d.cout > d.bn) return set_error("conv3x3: cout=%d vs bn=%d", d.cout, d.bn);
+  if (d.act < 0 || d.act > 2) return set_error("conv3x3: act=%d (0 none, 1 LeakyReLU(0.2), 2 ReLU)", d.act);
   for (int i = 0; i < d.num_chunks; ++i) {
     int s_ = d.chunk_src[i];
     if (s_ < 0 || s_ > 1 || !d.src[s_]) return set_error("conv3x3: chunk %d reads missing src %d", i, s_);

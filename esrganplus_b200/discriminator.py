@@ -100,6 +100,7 @@ class _Layer:
         self.bias_pad: Optional[torch.Tensor] = None
         self.w3: Optional[torch.Tensor] = None
         self.sig = None
+        self.act_code = 1   # fused activation of the bf16 output: 1 LeakyReLU(0.2) (this network), 2 ReLU (vgg_feature.py)
 
 
 class _Plan:
@@ -338,7 +339,7 @@ class DiscriminatorEngine:
                 call = K.ConvCall(n=n, h=gh, w=gw, srcs=[src], kc=L.kc, chunks=[(0, c0) for c0 in lc0], bn=SLICE,
                                   cout=SLICE, w_packed=tiles[s][g], w_layout=layout,
                                   bias=L.bias_pad[s * SLICE:(s + 1) * SLICE] if last else None,
-                                  act=1 if fused else 0)
+                                  act=L.act_code if fused else 0)
                 if fused:
                     call.out_bf16, call.ob_c0 = out_b, s * SLICE
                 else:

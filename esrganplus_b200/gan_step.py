@@ -7,7 +7,8 @@ restatement exists so that bench.py and the tests can drive the step on a box th
 On CUDA the solver arithmetic is native too (esrganplus_b200/solver.py): both Adam updates
 are one kernel each over flat parameter / gradient / moment buffers (``FlatAdam``, a ``torch.optim.Optimizer``, so the
 reference's ``MultiStepLR`` drives it), the relativistic BCE terms and the L1 loss are single launches with analytic
-gradients.  ``native_solver=False`` keeps torch's own Adam / BCE / L1 (what the reference runs).  With ``data_parallel``
+gradients.  With ``netF`` (a ``VGGFeatureExtractor``) the step also carries the perceptual term
+of the shipped recipe (``feature_weight`` 1, L1; SRRaGAN_model.py:127-131).  ``native_solver=False`` keeps torch's own Adam / BCE / L1 (what the reference runs).  With ``data_parallel``
 modules the two backward passes all-reduce their flat gradient buffers — nothing else is exchanged.
 """
 from __future__ import annotations
@@ -21,9 +22,10 @@ import torch.nn.functional as F
 class GanTrainStep:
     def __init__(self, netG, netD, lr_G: float = 1e-4, lr_D: float = 1e-4, beta1_G: float = 0.9, beta1_D: float = 0.9,
                  pixel_weight: float = 1e-2, gan_weight: float = 5e-3, weight_decay_G: float = 0.0,
-                 weight_decay_D: float = 0.0, native_solver: Optional[bool] = None, lr_steps=None, lr_gamma: float = 0.5):
-        self.netG, self.netD = netG, netD
-        self.l_pix_w, self.l_gan_w = pixel_weight, gan_weight
+                 weight_decay_D: float = 0.0, native_solver: Optional[bool] = None, lr_steps=None, lr_gamma: float = 0.5,
+                 netF=None, feature_weight: float = 1.0):
+        self.netG, self.netD, self.netF = netG, netD, netF
+        self.l_pix_w, self.l_gan_w, self.l_fea_w = pixel_weight, gan_weight, feature_weight
         on_cuda = all(p.is_cuda for p in netG.parameters())
         self.native = on_cuda if native_solver is None else bool(native_solver)
         pg = [p for p in netG.parameters() if p.requires_grad]
@@ -72,7 +74,17 @@ class GanTrainStep:
             l_g_pix = self.l_pix_w * F.l1_loss(self.fake_H, var_H)
             l_g_gan = self.l_gan_w * (self._gan(pred_d_real - torch.mean(pred_g_fake), False) +
                                       self._gan(pred_g_fake - torch.mean(pred_d_real), True)) / 2
-        (l_g_pix + l_g_gan).backward()
+        l_g_total = l_g_pix + l_g_gan
+        l_g_fea = None
+        if self.netF is not None:                                # SRRaGAN_model.py:127-131
+            real_fea = self.netF(var_H).detach()
+            fake_fea = self.netF(self.fake_H)
+            if self.native:
+                l_g_fea = self.l_fea_w * l1_loss(fake_fea, real_fea)
+            else:
+                l_g_fea = self.l_fea_w * F.l1_loss(fake_fea, real_fea)
+            l_g_total = l_g_total + l_g_fea
+        l_g_total.backward()
         self.optimizer_G.step()
         # ---- D (SRRaGAN_model.py:143-168)
         for p in netD.parameters():
@@ -92,4 +104,6 @@ class GanTrainStep:
         # the reference calls .item() on each of these (six host syncs per step, :171-186); kept as device scalars here
         self.log = {"l_g_pix": l_g_pix.detach(), "l_g_gan": l_g_gan.detach(), "l_d_real": l_d_real.detach(),
                     "l_d_fake": l_d_fake.detach(), "D_real": pred_d_real.detach().mean(), "D_fake": pred_d_fake.detach().mean()}
+        if l_g_fea is not None:
+            self.log["l_g_fea"] = l_g_fea.detach()
         return self.log

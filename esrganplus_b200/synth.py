@@ -69,3 +69,24 @@ def random_state_dict_d(in_nc: int = 3, base_nf: int = 64, seed: int = 0) -> Dic
     sd["classifier.2.weight"] = _u(rng, -0.1, 0.1, (1, 100))
     sd["classifier.2.bias"] = _u(rng, -0.1, 0.1, (1,))
     return sd
+
+
+def random_state_dict_vgg(feature_layer: int = 34, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Synthetic VGGFeatureExtractor weights (architecture.py:279-307; the pretrained torchvision file needs the network):
+    uniform with the kaiming bound so that the activations keep their scale through the sixteen layers."""
+    from .architecture import _VGG19_CFG
+    rng = np.random.default_rng(seed)
+    sd: Dict[str, torch.Tensor] = {"mean": torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1),
+                                   "std": torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)}
+    idx, cin = 0, 3
+    for v in _VGG19_CFG:
+        if v == "M":
+            idx += 1
+            continue
+        if idx <= feature_layer:
+            b = (6.0 / (cin * 9)) ** 0.5
+            sd[f"features.{idx}.weight"] = _u(rng, -b, b, (v, cin, 3, 3))
+            sd[f"features.{idx}.bias"] = _u(rng, -0.05, 0.05, (v,))
+        idx += 2
+        cin = v
+    return sd

@@ -88,7 +88,7 @@ typedef struct esrp_conv3x3 {
   const void* w_packed;         /* from esrp_pack_conv3x3_weights (incl. the conv1x1 rows)   */
   int32_t w_layout;             /* ESRP_LAYOUT_* the weights were packed for                 */
   const float* bias;            /* [bn] fp32 (zero padded), or NULL                          */
-  int32_t act;                  /* 0 none, 1 LeakyReLU(0.2)                                  */
+  int32_t act;                  /* 0 none, 1 LeakyReLU(0.2), 2 ReLU                          */
   float s0;
   const void* r1;               /* residual 1, NHWC [n,h,w,r1_ctotal], read at r1_c0..       */
   int32_t r1_is_f32, r1_ctotal, r1_c0;
@@ -267,6 +267,23 @@ int esrp_graph_launch(void* exec, void* stream);
 void esrp_graph_destroy(void* exec);
 /* cudaMemsetAsync(p, 0, bytes) as a recordable / capturable C-ABI call. */
 int esrp_memset_zero(void* p, int64_t bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Perceptual branch: VGGFeatureExtractor (architecture.py:279-307; csrc/esrp_vgg.cu).
+ * Its sixteen 3x3 convs run on esrp_conv3x3_nhwc with act = 2 (ReLU); these are the pieces between them.
+ * ------------------------------------------------------------------------------------------- */
+/* (x * scale[c] + shift[c]) -> NHWC bf16 padded to c_pad channels: `(x - mean) / std` of architecture.py:304-305 with
+ * scale = 1 / std, shift = -mean / std (both fp32 [c], or both NULL for a plain re-layout). */
+int esrp_nchw_f32_to_nhwc_bf16_affine(const float* src, const float* scale, const float* shift, void* dst, int32_t n, int32_t c,
+                                      int32_t h, int32_t w, int32_t c_pad, void* stream);
+/* nn.MaxPool2d(kernel_size=2, stride=2) on NHWC bf16 [n,h,w,c] -> [n,h/2,w/2,c] (h, w even, c % 8 == 0). */
+int esrp_maxpool2x2_nhwc_bf16(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, void* stream);
+/* dz = dy where y > 0 else 0; y = the ReLU's OUTPUT (bf16, count elements, count % 8 == 0). */
+int esrp_relu_bwd_nhwc_bf16(const void* y, const void* dy, void* dz, int64_t count, void* stream);
+/* Gradient through [ReLU, MaxPool2d(2,2)]: y [n,h,w,c] = the ReLU output that was pooled, dpool [n,h/2,w/2,c]; the first
+ * maximum of each window in torch's scan order receives dpool if it is positive, every other element gets 0. */
+int esrp_maxpool2x2_relu_bwd_nhwc_bf16(const void* y, const void* dpool, void* dz, int32_t n, int32_t h, int32_t w, int32_t c,
+                                       void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Training data path on the device (csrc/esrp_data.cu)

@@ -144,6 +144,58 @@ def discriminator_vgg128_forward(x: Tensor, sd: SD, training: bool = False,
     return t, new_buffers
 
 
+
+# torchvision.models.vgg19 configuration 'E' (the reference takes `model.features` of it, architecture.py:289,298):
+# out-channels per conv, 'M' = MaxPool2d(2, 2); every conv is 3x3 / stride 1 / pad 1 followed by ReLU(inplace)
+VGG19_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512, 512, 512, 512, "M"]
+
+
+def vgg19_feature_layout(feature_layer: int = 34):
+    """[(index in `features`, kind, cin, cout)] of torchvision's vgg19().features[:feature_layer + 1]
+    (architecture.py:298; feature_layer = 34 is conv5_4 BEFORE its ReLU, networks.py:144-148)."""
+    out, idx, cin = [], 0, 3
+    for v in VGG19_CFG:
+        if v == "M":
+            out.append((idx, "pool", cin, cin))
+            idx += 1
+        else:
+            out.append((idx, "conv", cin, v))
+            out.append((idx + 1, "relu", v, v))
+            idx += 2
+            cin = v
+    return [e for e in out if e[0] <= feature_layer]
+
+
+def vgg_feature_forward(x: Tensor, sd: SD, feature_layer: int = 34, use_input_norm: bool = True) -> Tensor:
+    """VGGFeatureExtractor.forward (architecture.py:303-307): (x - mean) / std, then features[:feature_layer + 1]."""
+    if use_input_norm:
+        x = (x - sd["mean"]) / sd["std"]                      # architecture.py:304-305
+    for idx, kind, _cin, _cout in vgg19_feature_layout(feature_layer):
+        if kind == "conv":
+            x = F.conv2d(x, sd[f"features.{idx}.weight"], sd[f"features.{idx}.bias"], stride=1, padding=1)
+        elif kind == "relu":
+            x = F.relu(x)
+        else:
+            x = F.max_pool2d(x, kernel_size=2, stride=2)
+    return x
+
+
+def synth_state_dict_vgg(feature_layer: int = 34, seed: int = 0) -> SD:
+    """Deterministic synthetic VGGFeatureExtractor weights (the pretrained torchvision file cannot be fetched here):
+    kaiming-uniform-like convs so that activations keep their scale through 16 layers, small biases of both signs."""
+    import numpy as np
+    rng = np.random.default_rng(seed + 4241)
+    sd: SD = {"mean": torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1),      # architecture.py:292
+              "std": torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)}        # architecture.py:294
+    for idx, kind, cin, cout in vgg19_feature_layout(feature_layer):
+        if kind != "conv":
+            continue
+        bound = (6.0 / (cin * 9)) ** 0.5
+        sd[f"features.{idx}.weight"] = torch.from_numpy(rng.uniform(-bound, bound, (cout, cin, 3, 3)).astype("float32"))
+        sd[f"features.{idx}.bias"] = torch.from_numpy(rng.uniform(-0.05, 0.05, (cout,)).astype("float32"))
+    return sd
+
+
 def psnr_255(a: Tensor, b: Tensor) -> float:
     """utils/util.py:107-114 — calculate_psnr on [0,255] images (here: clamp to [0,1], scale)."""
     a = a.clamp(0, 1) * 255.0

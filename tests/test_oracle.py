@@ -122,3 +122,22 @@ def test_oracle_gradients_match_reference_fixture(golden_dir):
 def test_golden_meta(golden_dir):
     meta = json.load(open(os.path.join(golden_dir, "meta.json")))
     assert meta["test_image_RRDB_Net_equals_RRDBNet_eval"] and meta["test_image_keys_equal"]
+
+
+def test_vgg_feature_oracle_matches_reference_fixture(golden_dir):
+    """oracle.vgg_feature_forward against features, L1 feature loss and input gradient produced by the reference's own
+    VGGFeatureExtractor (tests/golden/make_golden_vgg.py)."""
+    import numpy as np
+    d = np.load(os.path.join(golden_dir, "vgg_feature_34.npz"))
+    sd = O.synth_state_dict_vgg(34, seed=3)
+    fake = torch.from_numpy(d["fake"]).requires_grad_(True)
+    fea = O.vgg_feature_forward(fake, sd)
+    real_fea = O.vgg_feature_forward(torch.from_numpy(d["real"]), sd).detach()
+    for got, key in ((fea.detach(), "fake_fea"), (real_fea, "real_fea")):
+        ref = torch.from_numpy(d[key])
+        assert (got - ref).abs().max().item() <= 2e-6 * ref.abs().max().item() + 1e-6
+    loss = torch.nn.functional.l1_loss(fea, real_fea)
+    assert abs(loss.item() - float(d["loss"])) <= 1e-6
+    loss.backward()
+    ref = torch.from_numpy(d["dfake"])
+    assert (fake.grad - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()

@@ -216,3 +216,25 @@ def test_optimizer_steps_invalidate_the_derived_weight_cache():
         opt_d = torch.optim.SGD(d.parameters(), lr=0.1)
         opt_d.step()
         assert d.weights_epoch > e_d
+
+
+def test_vgg_feature_extractor_structure_matches_reference_fixture(golden_dir):
+    """Keys and str(net) stored by tests/golden/make_golden_vgg.py from the reference's own VGGFeatureExtractor
+    (architecture.py:279-307); frozen feature weights (:299-301); a torchvision vgg19 state_dict loads by key."""
+    import numpy as np
+    d = np.load(os.path.join(golden_dir, "vgg_feature_34.npz"))
+    m = E.VGGFeatureExtractor(feature_layer=34, use_bn=False, use_input_norm=True, device=torch.device("cpu"))
+    assert list(m.state_dict().keys()) == [str(k) for k in d["keys"]]
+    assert str(m) == str(d["repr"])
+    assert not any(p.requires_grad for p in m.parameters())
+    tv = {k: torch.full_like(v, 0.5) for k, v in m.state_dict().items() if k.startswith("features.")}
+    tv["features.35.weight"] = torch.zeros(1)          # layers beyond the cut and the classifier are ignored
+    tv["classifier.0.weight"] = torch.zeros(1)
+    m.load_vgg19_state_dict(tv)
+    assert float(m.features[34].weight.mean()) == 0.5 and float(m.mean.flatten()[0]) == pytest.approx(0.485)
+    with pytest.raises(KeyError):
+        m.load_vgg19_state_dict({"features.0.weight": tv["features.0.weight"]})
+    with pytest.raises(NotImplementedError):
+        E.VGGFeatureExtractor(use_bn=True)
+    with pytest.raises(RuntimeError):
+        m(torch.rand(1, 3, 32, 32))                    # no CPU fallback
