@@ -13,7 +13,8 @@ Inference shards independent tiles across ranks with no collective (weak scaling
 `roofline`   the conv3x3 tcgen05 kernel family = every launch of the step but three small
              layout kernels; achieved = algorithmic FLOPs of the step / event time of the step.
 `train`      secondary leg, BASELINE.json config 4: ESRGAN+ GAN train step imgs/s, 32 crops per GPU (weak scaling),
-             gradient all-reduce over NCCL; `train_strong` (N > 1 only): the same with 32 crops in total; see train_leg().
+             gradient all-reduce over NCCL; `train_strong` (N > 1 only): the same with 32 crops in total; `train_perceptual`:
+             the weak leg with the VGG19 feature loss of the shipped recipe added; see train_leg().
 `cpu_baseline` / --impl reference: the reference's algorithm (CPU oracle = torch CPU fp32 ops, the
              same ATen kernels the reference's nn.Conv2d dispatches to) on this box's host cores, on
              a bounded sample (one 128x128 tile per step).
@@ -182,7 +183,7 @@ def main_reference(args):
     }))
 
 
-def train_leg(torch, dev, world, rank, dist, steps=8, warmup=3, global_batch=32, scaling="strong"):
+def train_leg(torch, dev, world, rank, dist, steps=8, warmup=3, global_batch=32, scaling="strong", perceptual=False):
     """BASELINE.json config 4: one ESRGAN+ GAN step (RRDBNet nb=23 nf=64 G + Discriminator_VGG_128 D, no perceptual,
     SRRaGAN_model.py:113-186) on 128x128 HR / 32x32 LR synthetic crops; `global_batch` is split across ranks and the
     two backward passes all-reduce their flat gradient buffers over NCCL.  imgs/s from CUDA events, max over ranks.
@@ -191,7 +192,7 @@ def train_leg(torch, dev, world, rank, dist, steps=8, warmup=3, global_batch=32,
     import esrganplus_b200 as E
     from esrganplus_b200.autograd import broadcast_parameters, data_parallel
     from esrganplus_b200.gan_step import GanTrainStep
-    from esrganplus_b200.synth import random_state_dict_d, random_state_dict_g
+    from esrganplus_b200.synth import random_state_dict_d, random_state_dict_g, random_state_dict_vgg
     bs = max(1, global_batch // world)
     netG = E.RRDBNet(3, 3, NF, NB)
     # ~ kaiming x 0.1 with zero bias, what networks.py:103-104 does for G before training
@@ -204,7 +205,12 @@ def train_leg(torch, dev, world, rank, dist, steps=8, warmup=3, global_batch=32,
         broadcast_parameters(netD)
         data_parallel(netG)
         data_parallel(netD)
-    step = GanTrainStep(netG, netD)
+    netF = None
+    if perceptual:   # the shipped recipe's feature loss (train_ESRGANplus.json: feature_weight 1, l1; VGG19 conv5_4, frozen)
+        netF = E.VGGFeatureExtractor(feature_layer=34, use_bn=False, use_input_norm=True)
+        netF.load_state_dict(random_state_dict_vgg(34, seed=33), strict=True)
+        netF = netF.to(dev).eval()
+    step = GanTrainStep(netG, netD, netF=netF)
     g = torch.Generator().manual_seed(100 + rank)
     lr = torch.rand(bs, 3, 32, 32, generator=g).to(dev)
     hr = torch.rand(bs, 3, 128, 128, generator=g).to(dev)
@@ -235,11 +241,12 @@ def train_leg(torch, dev, world, rank, dist, steps=8, warmup=3, global_batch=32,
     return {"metric": "gan_train_imgs_per_sec", "value": bs * world * steps / (ms * 1e-3), "unit": "imgs/s",
             "ms_per_step": ms / steps, "host_issue_ms_per_step": host_ms, "steps": steps, "warmup": warmup,
             "global_batch": bs * world, "batch_per_gpu": bs, "scaling": scaling, "losses_finite": finite,
-            "workload": "ESRGAN+ GAN step, RRDBNet nb=23 nf=64 + Discriminator_VGG_128, 128x128 HR crops, no perceptual (config 4)",
+            "workload": "ESRGAN+ GAN step, RRDBNet nb=23 nf=64 + Discriminator_VGG_128, 128x128 HR crops, " +
+                        ("with the VGG19 feature loss (the shipped recipe; config 4 + SURVEY 8f-1)" if perceptual else "no perceptual (config 4)"),
             "collective": None if dist is None else "all-reduce(avg) of the flat G (67.4 MB) and D (58.0 MB) gradient buffers, NCCL",
             "generator_launches_fwd_bwd": [fl, bl],
-            "flops_per_img_algorithmic": 151e9,
-            "achieved_tflops_per_gpu": 151e9 * bs * steps / (ms * 1e-3) / 1e12}
+            "flops_per_img_algorithmic": 151e9 + (3 * 12.7e9 if perceptual else 0.0),
+            "achieved_tflops_per_gpu": (151e9 + (3 * 12.7e9 if perceptual else 0.0)) * bs * steps / (ms * 1e-3) / 1e12}
 
 
 def main_ours(args):
@@ -408,7 +415,7 @@ def main_ours(args):
                 lib_leg = gpu_library_baseline(torch, dev, sd, x_dev)
             except Exception as e:
                 lib_leg = {"error": f"{type(e).__name__}: {e}"[:300]}
-    train = train_strong = None
+    train = train_strong = train_perceptual = None
     if not args.no_train:
         # the inference legs leave ~2.5 GB of cached workspace behind and the GPU at its power cap: hand the memory back and
         # let the clocks settle before the secondary measurement
@@ -423,6 +430,10 @@ def main_ours(args):
                 train_strong = train_leg(torch, dev, world, rank, dist, global_batch=32, scaling="strong")
         except Exception as e:  # the headline line must survive a failure of the secondary leg
             train = train or {"error": f"{type(e).__name__}: {e}"[:300]}
+        try:
+            train_perceptual = train_leg(torch, dev, world, rank, dist, global_batch=32 * world, scaling="weak", perceptual=True)
+        except Exception as e:
+            train_perceptual = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     launches = launches_plain
     per_step = ms / args.steps
@@ -486,6 +497,7 @@ def main_ours(args):
             "attempts": 1,
             "train": train,
             "train_strong": train_strong,
+            "train_perceptual": train_perceptual,
         }
         print(json.dumps(line))
     if dist is not None:

@@ -23,12 +23,13 @@ def main():
     ap.add_argument("--nb", type=int, default=23)
     ap.add_argument("--weak", action="store_true")
     ap.add_argument("--phases", action="store_true", help="time G fwd / G bwd / D separately (adds syncs)")
+    ap.add_argument("--perceptual", action="store_true", help="add the VGG19 feature loss of the shipped recipe (feature_weight 1)")
     args = ap.parse_args()
     import torch
     import esrganplus_b200 as E
     from esrganplus_b200.autograd import data_parallel
     from esrganplus_b200.gan_step import GanTrainStep
-    from esrganplus_b200.synth import random_state_dict_d, random_state_dict_g
+    from esrganplus_b200.synth import random_state_dict_d, random_state_dict_g, random_state_dict_vgg
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -48,7 +49,12 @@ def main():
     if world > 1:
         data_parallel(netG)
         data_parallel(netD)
-    step = GanTrainStep(netG, netD)
+    netF = None
+    if args.perceptual:
+        netF = E.VGGFeatureExtractor()
+        netF.load_state_dict(random_state_dict_vgg(34, seed=33))
+        netF = netF.to(dev).eval()
+    step = GanTrainStep(netG, netD, netF=netF)
     g = torch.Generator().manual_seed(rank)
     lr = torch.rand(bs, 3, 32, 32, generator=g).to(dev)
     hr = torch.rand(bs, 3, 128, 128, generator=g).to(dev)
@@ -77,7 +83,26 @@ def main():
     out = {"metric": "gan_train_imgs_per_sec", "value": bs * world * args.steps / (ms * 1e-3), "unit": "imgs/s", "n_gpus": world,
            "batch_per_gpu": bs, "steps": args.steps, "ms_per_step": ms / args.steps,
            "host_issue_ms_per_step": t_host / args.steps * 1e3, "nb": args.nb,
-           "scaling": "weak" if args.weak else "strong", "finite": bool(torch.isfinite(step.log["l_d_real"]).item())}
+           "scaling": "weak" if args.weak else "strong", "finite": bool(torch.isfinite(step.log["l_d_real"]).item()),
+           "perceptual": bool(args.perceptual)}
+    if netF is not None:   # the feature extractor on its own: forward, and forward + input gradient (12.7 GFLOP / image / pass)
+        def tf(fn, reps=10):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        with torch.no_grad():
+            f_ms = tf(lambda: netF(hr))
+        hrg = hr.clone().requires_grad_(True)
+        fb_ms = tf(lambda: netF(hrg).sum().backward())
+        out["vgg19"] = {"fwd_ms": round(f_ms, 3), "fwd_bwd_ms": round(fb_ms, 3), "fwd_tflops": round(12.7e9 * bs / (f_ms * 1e-3) / 1e12, 1),
+                        "fwd_bwd_tflops": round(2 * 12.7e9 * bs / (fb_ms * 1e-3) / 1e12, 1)}
     if args.phases:
         def timed(fn):
             torch.cuda.synchronize()
