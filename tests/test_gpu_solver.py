@@ -112,10 +112,14 @@ def test_gan_step_native_solver_matches_torch_solver(cuda_dev):
                 assert torch.allclose(moved[big], torch.full_like(moved[big], 1e-4), rtol=2e-2), k
                 assert ((p.detach() - p0[k])[big].sign() == -gr[big].sign()).all(), k
     assert sa.optimizer_G.param_groups[0]["lr"] == pytest.approx(5e-5)   # MultiStepLR halved it after step 1
+    far = total = 0
     for (k, p), (_, q) in list(zip(Ga.named_parameters(), Gb.named_parameters())) + list(zip(Da.named_parameters(), Db.named_parameters())):
         # After the first step the two runs' parameters differ in the last bit here and there, the bf16 weight tiles then
         # round differently, and the second step's gradients differ by a per cent or so: elements move by up to a fifth of a
         # learning rate apart (measured: 5e-5 at most, 8 % of the elements by more than 3e-6); an element whose gradient is
         # rounding noise around zero may go the other way altogether (2 lr).
         d = (p.detach() - q.detach()).abs()
-        assert d.max().item() <= 2.1e-4 and (d > 2e-5).float().mean().item() <= 2e-2, (k, d.max().item(), (d > 2e-5).float().mean().item())
+        assert d.max().item() <= 2.1e-4, (k, d.max().item())
+        far += int((d > 2e-5).sum().item())
+        total += d.numel()
+    assert far <= 2e-2 * total, (far, total)   # (over all parameters: one element of a 32-element bias is already 3 %)
