@@ -27,7 +27,7 @@ def variant_cwlog2(l: int) -> int:
     return (l & 15) << 4
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libesrp.so")
+LIB_PATH = os.environ.get("ESRP_LIBRARY") or os.path.join(_HERE, "libesrp.so")   # (ESRP_LIBRARY: A/B runs of two builds)
 
 
 class Conv3x3Desc(C.Structure):

@@ -43,6 +43,13 @@
 //             slice, so the rows are fetched from DRAM once and every CTA owns nsl times more rows.
 #pragma once
 #ifndef ESRP_SYNCCHECK_PAD
+// Per-row timeline events of the issuer / epilogue / producer of CTA 0 (tools/trace_conv.py): compiled in with
+// -DESRP_TRACE_FINE only, they sit in the issuing thread's instruction stream.
+#ifdef ESRP_TRACE_FINE
+#define ESRP_FINE_TRACE(stmt) stmt
+#else
+#define ESRP_FINE_TRACE(stmt)
+#endif
 #define ESRP_SYNCCHECK_PAD 0  // experiment (tools/gpu_r2_p.sh): move tok[] off shared-memory offset 0x148
 #endif
 #include <cuda.h>
@@ -147,6 +154,10 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  // slots 1019..1023 of the epilogue's trace row: clock64 / %globaltimer at kernel entry, at the start of the role loops, at exit
+  ESRP_FINE_TRACE(if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) { p.trace[2 * 1024 + 1023] = clock64(); long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); p.trace[2 * 1024 + 1022] = gt; })
+  // per-CTA %globaltimer at entry (row 0, slots 512 + CTA) and exit (row 1): launch-to-launch gaps, tools/trace_gap.py
+  ESRP_FINE_TRACE(if (p.trace && threadIdx.x == 0 && blockIdx.x < 512) { long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); p.trace[512 + blockIdx.x] = gt; })
 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);   // [kMaxStages] one per row buffer
   uint64_t* blk_full = full_bar + kMaxStages;               // [kMaxBlocks] block complete (2 issuer commits)
@@ -218,6 +229,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
   __syncthreads();
   tcgen05_fence_after();
 
+  ESRP_FINE_TRACE(if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[2 * 1024 + 1019] = clock64();)
   // ring position (block index) of output sequence number O: descending, so that the blocks of the output
   // rows r+1, r, r-1 an input row r accumulates into are adjacent with ascending columns (ky = 0, 1, 2)
   auto pos = [](uint32_t O) -> uint32_t { return (NBLK - 1) - (O & (NBLK - 1)); };
@@ -248,6 +260,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
         const int r0 = max(sw.ya - 1, 0), r1 = min(sw.yb, p.h - 1);
         for (int r = r0; r <= r1; ++r, ++I) {
           if (I >= static_cast<uint32_t>(D)) mbar_wait(&blk_full[buf_bar[b]], buf_par[b]);
+          ESRP_FINE_TRACE(trace_ev(p, 0, tn);)  // buffer free, TMA issued next
           const uint32_t Oc = O0 + (r - r0);  // the output row this input row completes
           buf_bar[b] = pos(Oc);
           buf_par[b] = use(Oc);
@@ -291,6 +304,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
       const int ni = min(sw.yb, p.h - 1) - max(sw.ya - 1, 0) + 1;
       for (int k = 0; k < ni; ++k) {
         mbar_wait(&full_bar[b], fph);
+        ESRP_FINE_TRACE(if (mw == 0 && lane == 0 && (I & 1u) == 0u) trace_ev(p, 1, tn);)  // full_bar ok (own rows)
         // blocks first touched by this input row must have been read + zeroed by their previous occupant
         const uint32_t On = O0 + k + 2;  // output row r+1 (ky = 0): always new
         if (k == 0) {
@@ -317,7 +331,9 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
           // from the issuer of its middle row r (commits only track the committing thread's MMAs; rows r-1 and r+1
           // belong to the same warp).  Segment ends: the missing contributor's commit is issued by the same thread.
           if ((I & 1u) == static_cast<uint32_t>(mw)) {
+            ESRP_FINE_TRACE(if (mw == 0 && lane == 0) trace_ev(p, 1, tn);)  // waits done
             mbar_wait(&tok[mw], tph);
+            ESRP_FINE_TRACE(if (mw == 0 && lane == 0) trace_ev(p, 1, tn);)  // turn taken
             if (elect_one()) {
               uint32_t al = a_lo, bl = w_lo0;
               for (int c = 0; c < nfull; ++c, al += chunk_step, bl += w_step) {
@@ -349,6 +365,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
                                  (c | ks) != 0 ? 1u : 0u);
                 }
               }
+              ESRP_FINE_TRACE(if (mw == 0) trace_ev(p, 1, tn);)  // MMAs issued
               mbar_arrive(&tok[mw ^ 1]);                // the other warp's turn
               umma_commit(&blk_full[pos(O0 + k)]);      // final contributor of output row r-1
               umma_commit(&blk_full[pos(O0 + k + 1)]);  // middle contributor of output row r
@@ -360,6 +377,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
               }
             }
             __syncwarp();
+            ESRP_FINE_TRACE(if (mw == 0 && lane == 0) trace_ev(p, 1, tn);)  // committed
             tph ^= 1;
           } else if (p.row_alt == 2) {
             // The idle warp has now observed every barrier of row I as well.  Its arrival keeps the block (and, through
@@ -475,7 +493,9 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
           if (p.r1) load_residual<GC>(p.r1, p.r1_is_f32, off_res(p.r1_is_f32, p.r1_ctotal, p.r1_c0 + csh), r1v, f4_step);
           if (p.r2) load_residual<GC>(p.r2, p.r2_is_f32, off_res(p.r2_is_f32, p.r2_ctotal, p.r2_c0 + csh), r2v, f4_step);
         }
+        ESRP_FINE_TRACE(if (threadIdx.x == 0) trace_ev(p, 2, tn);)  // row start
         mbar_wait(&blk_full[pos(O)], use(O));
+        ESRP_FINE_TRACE(if (threadIdx.x == 0) trace_ev(p, 2, tn);)  // blk_full ok
         tcgen05_fence_after();
         if (!real) {  // dummy row at a segment end: just recycle the block
 #pragma unroll
@@ -505,6 +525,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&blk_empty[pos(O)]);
+            ESRP_FINE_TRACE(if (threadIdx.x == 0) trace_ev(p, 2, tn);)  // block released
           }
           if (ch0 >= p.cout) continue;  // (warp-uniform; lanes of columns >= w compute along and store nothing)
           const int gch = ch0 + csh;  // channel relative to the *_c0 offsets of the descriptor
@@ -646,6 +667,8 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  ESRP_FINE_TRACE(if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) { p.trace[2 * 1024 + 1021] = clock64(); long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); p.trace[2 * 1024 + 1020] = gt; })
+  ESRP_FINE_TRACE(if (p.trace && threadIdx.x == 0 && blockIdx.x < 512) { long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); p.trace[1024 + 512 + blockIdx.x] = gt; })
 }
 
 }  // namespace esrp

@@ -58,6 +58,11 @@ def run(name, n=16, h=128, w=128, variant=0, iters=50):
     call.launch()
     torch.cuda.synchronize()
     t = tr.cpu().view(3, 1024)
+    if int(t[2][1023]) > 0:   # -DESRP_TRACE_FINE builds: kernel entry / role-loop start / exit of CTA 0
+        c_in, g_in, c_out, g_out, c_loop = (int(t[2][i]) for i in (1023, 1022, 1021, 1020, 1019))
+        print(f"  CTA 0: entry -> role loops {c_loop - c_in} cycles, entry -> exit {c_out - c_in} cycles = {g_out - g_in} ns "
+              f"({(c_out - c_in) / max(1, g_out - g_in):.2f} GHz); launch-to-launch {us * 1000:.0f} ns")
+        t[2][1019:] = 0
     t0 = min(int(t[r][0]) for r in range(3) if int(t[r][0]) > 0)
     print(f"== {name} variant={variant} chunks={len(chunks)} kc={kc} bn={bn}")
     for r, role in enumerate(["producer(start, then after each empty-wait)", "mma(start; per chunk: full ok, q_empty ok, mmas issued, committed)",
@@ -65,7 +70,7 @@ def run(name, n=16, h=128, w=128, variant=0, iters=50):
         ev = [int(v) - t0 for v in t[r] if int(v) > 0]
         print(role)
         print("  abs:", ev[:40])
-        print("  dlt:", [b - a for a, b in zip(ev[:-1], ev[1:])][:40])
+        print("  dlt:", [b - a for a, b in zip(ev[:-1], ev[1:])][:60])
 
 
 if __name__ == "__main__":

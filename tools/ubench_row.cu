@@ -9,7 +9,7 @@
 #include "../esrganplus_b200/csrc/esrp_ptx.cuh"
 using namespace esrp;
 
-struct Cfg { int n, sbo, dstride, nslots, chunks, commit_every, stage_bytes, kx_shift, same_stage, issuers, interleave; };
+struct Cfg { int n, sbo, dstride, nslots, chunks, commit_every, stage_bytes, kx_shift, same_stage, issuers, interleave, loop_mode; };
 
 __global__ void __launch_bounds__(128, 1) k(Cfg c, int rows, long long* out) {
   extern __shared__ uint8_t smem_raw[];
@@ -34,6 +34,36 @@ __global__ void __launch_bounds__(128, 1) k(Cfg c, int rows, long long* out) {
     for (int rep = -1; rep < 4; ++rep) {
       if (rep == 0) t0 = clock64();
       int s = 0, slot = 0, cnt = 0;
+      if (c.loop_mode == 1) {
+        // ONE elected thread runs the whole row loop (no per-row elect / reconvergence)
+        if (elect_one()) {
+          for (int r = 0; r < rows; ++r) {
+            if ((r % c.issuers) != warp) { if (++slot == c.nslots) slot = 0; s = (s + c.chunks) % 8; continue; }
+            for (int ch = 0; ch < c.chunks; ++ch) {
+              const uint32_t a_lo = alo0 + ((c.same_stage ? 0 : s) * c.stage_bytes >> 4);
+              const uint32_t b_lo = blo0 + ((ch * 3 * c.n * 128) >> 4);
+              const uint32_t bstep = (c.n * 128) >> 4, astep = c.kx_shift >> 4;
+              const uint32_t d = tmem + slot * c.dstride;
+              ++cnt;
+#pragma unroll
+              for (int kk = 0; kk < 3; ++kk) {
+                const int kx = kk == 0 ? 1 : (kk == 1 ? 0 : 2);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_f16_ss2(d, a_lo + kx * astep + ks * 2, ahi, b_lo + kx * bstep + ks * 2, bhi, idesc, (ch | kk | ks) != 0);
+              }
+              if (c.commit_every && (cnt % c.commit_every) == 0) umma_commit(bar + 1);
+              if (++s == 8) s = 0;
+            }
+            if (++slot == c.nslots) slot = 0;
+          }
+          umma_commit(bar);
+        }
+        __syncwarp();
+        mbar_wait(bar, (rep + 1) & 1);
+        tcgen05_fence_after();
+        continue;
+      }
       for (int r = 0; r < rows; ++r) {
         if ((r % c.issuers) != warp) { if (++slot == c.nslots) slot = 0; s = (s + c.chunks) % 8; continue; }
         for (int ch = 0; ch < c.chunks; ++ch) {
@@ -53,7 +83,7 @@ __global__ void __launch_bounds__(128, 1) k(Cfg c, int rows, long long* out) {
             }
             if (c.commit_every && (cnt % c.commit_every) == 0) umma_commit(bar + 1);
           }
-          __syncwarp();
+          if (c.loop_mode != 2) __syncwarp();
           if (++s == 8) s = 0;
         }
         if (++slot == c.nslots) slot = 0;
@@ -104,5 +134,12 @@ int main() {
   run("2 issuers, sliding D, two interleaved rings, 2 chunks", {96, 1024, 32, 6, 2, 2, 17408, 128, 0, 2, 1});
   run("1 issuer, sliding D, two interleaved rings", {96, 1024, 32, 6, 1, 1, 17408, 128, 0, 1, 1});
   run("2 issuers, disjoint D stride 96, 2 chunks", {96, 1024, 96, 5, 2, 2, 17408, 128, 0, 2});
+  // round 2: what does the per-row elect / reconvergence cost a single issuer?
+  run("1 issuer, sliding D, one elected thread runs the row loop", {96, 1024, 32, 14, 1, 1, 17408, 128, 0, 1, 0, 1});
+  run("1 issuer, sliding D, one elected thread, no commit",        {96, 1024, 32, 14, 1, 0, 17408, 128, 0, 1, 0, 1});
+  run("1 issuer, sliding D, elect per row without syncwarp",       {96, 1024, 32, 14, 1, 1, 17408, 128, 0, 1, 0, 2});
+  run("1 issuer, sliding D, one elected thread, 2 chunks",         {96, 1024, 32, 14, 2, 2, 17408, 128, 0, 1, 0, 1});
+  run("1 issuer, sliding D, one elected thread, 3 chunks",         {96, 1024, 32, 14, 3, 3, 17408, 128, 0, 1, 0, 1});
+  run("1 issuer, sliding D (stride 32), 3 chunks",                 {96, 1024, 32, 14, 3, 3, 17408, 128, 0, 1});
   return 0;
 }
