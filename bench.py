@@ -183,7 +183,7 @@ def main_reference(args):
     }))
 
 
-def train_leg(torch, dev, world, rank, dist, steps=8, warmup=3, global_batch=32, scaling="strong", perceptual=False):
+def train_leg(torch, dev, world, rank, dist, steps=8, warmup=5, global_batch=32, scaling="strong", perceptual=False):
     """BASELINE.json config 4: one ESRGAN+ GAN step (RRDBNet nb=23 nf=64 G + Discriminator_VGG_128 D, no perceptual,
     SRRaGAN_model.py:113-186) on 128x128 HR / 32x32 LR synthetic crops; `global_batch` is split across ranks and the
     two backward passes all-reduce their flat gradient buffers over NCCL.  imgs/s from CUDA events, max over ranks.

@@ -14,6 +14,9 @@ SHAPES = {
     "conv3": (64, [(0, 0), (1, 0)], 32, 32, 0),
     "conv5h": (64, [(0, 0), (1, 0), (1, 64)], 32, 32, 0),
     "hr1": (64, [(0, 0)], 16, 3, 0),
+    # the growth chunk read from a 64-channel tensor (a pixel's 128 bytes contiguous with its neighbours') instead of one half
+    # of the 128-channel growth buffer (128 of every 256 bytes): does the strided fetch cost DRAM efficiency?
+    "conv3c": (64, [(0, 0), (1, 0)], 32, 32, 0),
 }
 LAYOUT = int(os.environ.get("ESRP_LAYOUT", "1"))
 
@@ -22,7 +25,7 @@ def run(name, n=16, h=128, w=128, variant=0, iters=50):
     kc, chunks, bn, cout, aux = SHAPES[name]
     dev = "cuda"
     s0 = torch.randn(n, h, w, 64, device=dev).to(torch.bfloat16)
-    s1 = torch.randn(n, h, w, 128, device=dev).to(torch.bfloat16)
+    s1 = torch.randn(n, h, w, 64 if name.endswith("c") else 128, device=dev).to(torch.bfloat16)
     cin = kc * len(chunks)
     wt = torch.randn(cout, cin, 3, 3, device=dev) * 0.02
     wp = K.pack_conv3x3_weights(wt, kc, bn, [i * kc for i in range(len(chunks))], layout=LAYOUT)
