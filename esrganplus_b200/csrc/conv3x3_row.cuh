@@ -192,7 +192,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
   if (warp == kRowEpiWarps && lane == 0) {
     tma_prefetch_desc(&tm0);
     tma_prefetch_desc(&tm1);
-    for (int i = 0; i < D; ++i) mbar_init(&full_bar[i], 1);
+    for (int i = 0; i < (p.chunk_bars ? D * p.num_chunks : D); ++i) mbar_init(&full_bar[i], 1);
     for (int i = 0; i < kMaxBlocks; ++i) {
       // row-alternating issue (row_alt == 2): + one plain arrival of the warp that does NOT issue the completing row
       mbar_init(&blk_full[i], p.row_alt == 2 ? kRowMmaWarps + 1 : kRowMmaWarps);
@@ -270,10 +270,18 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
             if (++b == D) { b = 0; st = stage0; }
             continue;
           }
-          mbar_arrive_expect_tx(&full_bar[b], tx_bytes);
-          for (int c = 0; c < nch; ++c)
-            tma_load_4d_hint(st + c * a_bytes, p.chunk_src[c] ? &tm1 : &tm0, &full_bar[b], p.chunk_c0[c], sw.x0 - 1, r,
-                             sw.img, kL2EvictLast);  // bf16 activations are re-read by the next convs: keep in L2
+          if (p.chunk_bars) {  // one barrier per chunk tile: full_bar[b * nch + c]
+            for (int c = 0; c < nch; ++c) {
+              mbar_arrive_expect_tx(&full_bar[b * nch + c], static_cast<uint32_t>(p.a_box_bytes));
+              tma_load_4d_hint(st + c * a_bytes, p.chunk_src[c] ? &tm1 : &tm0, &full_bar[b * nch + c], p.chunk_c0[c], sw.x0 - 1, r,
+                               sw.img, kL2EvictLast);
+            }
+          } else {
+            mbar_arrive_expect_tx(&full_bar[b], tx_bytes);
+            for (int c = 0; c < nch; ++c)
+              tma_load_4d_hint(st + c * a_bytes, p.chunk_src[c] ? &tm1 : &tm0, &full_bar[b], p.chunk_c0[c], sw.x0 - 1, r,
+                               sw.img, kL2EvictLast);  // bf16 activations are re-read by the next convs: keep in L2
+          }
           st += row_bytes;
           if (++b == D) { b = 0; st = stage0; }
         }
@@ -303,7 +311,9 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     while (sw.next(p)) {
       const int ni = min(sw.yb, p.h - 1) - max(sw.ya - 1, 0) + 1;
       for (int k = 0; k < ni; ++k) {
-        mbar_wait(&full_bar[b], fph);
+        // chunk_bars: both warps meet the row's FIRST chunk barrier here (like the row barrier), the issuing thread the others
+        // inside its issue loop (tests/test_row_protocol_model.py::test_chunk_barriers_are_live_and_safe).
+        mbar_wait(&full_bar[p.chunk_bars ? b * nch : b], fph);
         ESRP_FINE_TRACE(if (mw == 0 && lane == 0 && (I & 1u) == 0u) trace_ev(p, 1, tn);)  // full_bar ok (own rows)
         // blocks first touched by this input row must have been read + zeroed by their previous occupant
         const uint32_t On = O0 + k + 2;  // output row r+1 (ky = 0): always new
@@ -337,6 +347,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
             if (elect_one()) {
               uint32_t al = a_lo, bl = w_lo0;
               for (int c = 0; c < nfull; ++c, al += chunk_step, bl += w_step) {
+                if (p.chunk_bars && c > 0) { mbar_wait(&full_bar[b * nch + c], fph); tcgen05_fence_after(); }
                 if (nB == 0) {
                   issue_taps<KC, BN, 0, false>(dA, dB, idA, idB, bB, al, bl, DESC_HI, w_block_desc);
                   issue_taps<KC, BN, 1, false>(dA, dB, idA, idB, bB, al, bl, DESC_HI, w_block_desc);
@@ -345,6 +356,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
                   issue_taps<KC, BN, 1, true>(dA, dB, idA, idB, bB, al, bl, DESC_HI, w_block_desc);
                 }
               }
+              if (p.chunk_bars && nfull < nch && nfull > 0) { mbar_wait(&full_bar[b * nch + nfull], fph); tcgen05_fence_after(); }
               if (nfull < nch) {  // last chunk: only its first half carries weights (K = 96 / 160 in 64-channel chunks)
                 if (nB == 0) {
                   issue_taps<KC, BN, 0, false, KS / 2>(dA, dB, idA, idB, bB, al, bl, DESC_HI, w_block_desc);

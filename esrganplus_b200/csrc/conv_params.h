@@ -62,6 +62,8 @@ struct ConvKParams {
   int last_half;           // row kernel (row_alt): only the first kc/2 channels of the last chunk carry weights
   int row_alt;             // row kernel: the two MMA issuers alternate whole rows instead of splitting the taps of every row
   int no_quad;             // row kernel: store bf16 outputs pixel by pixel (timing experiments: ESRP_NO_QUAD)
+  int chunk_bars;          // row kernel (row_alt, even ring depth, stages * num_chunks <= 8): one "data landed" barrier per K-chunk
+                           // tile instead of one per row, so the MMAs of chunk c start when chunk c is there
   int dbg;           // timing experiments only (ESRP_DBG_*): results are wrong when non-zero
   long long* trace;  // optional [3][1024] clock64 timeline of CTA 0 (see trace_ev)
 };

@@ -30,9 +30,13 @@ class Bar:
 
 
 class Model:
-    def __init__(self, mode, nblk, stages, segments, rng):
+    def __init__(self, mode, nblk, stages, segments, rng, chunks=1):
+        """chunks > 1: one "landed" barrier per K-chunk tile of a row buffer (ConvKParams::chunk_bars, row-alternating modes
+        with an even ring depth): both warps meet the first chunk's barrier of every row, the issuing thread the others."""
         self.mode, self.nblk, self.D, self.segs, self.rng = mode, nblk, stages, segments, rng
-        self.full = [Bar(1) for _ in range(stages)]
+        self.nch = chunks
+        self.full = [Bar(1) for _ in range(stages * chunks)]
+        self.tile_row = [None] * (stages * chunks)   # global row whose chunk has LANDED in a tile
         self.blk_full = [Bar(3 if mode == 2 else 2) for _ in range(nblk)]
         self.blk_empty = [Bar(1) for _ in range(nblk)]      # the 4 warps of a warpgroup modelled as one arrival
         self.tok = [Bar(1), Bar(1)]
@@ -69,7 +73,8 @@ class Model:
                 oc = O0 + k
                 buf_bar[b], buf_par[b] = self.pos(oc), self.use(oc)
                 self.buf_row[b] = I
-                self.tma.append((b, I))
+                for c in range(self.nch):
+                    self.tma.append((b * self.nch + c, I))
                 yield None
                 I, b = I + 1, (b + 1) % self.D
             O0 += ni + 2
@@ -78,7 +83,7 @@ class Model:
         b, fph, tph, O0, I = 0, 0, 0, 0, 0
         for ni in self.segs:
             for k in range(ni):
-                fb = self.full[b]
+                fb = self.full[b * self.nch]
                 yield lambda fb=fb, fph=fph: fb.passed(fph)
                 news = [O0 + k + 2] + ([O0, O0 + 1] if k == 0 else [])
                 for o in news:
@@ -97,6 +102,12 @@ class Model:
                             self.blk_owner[self.pos(o)] = o
                     if self.buf_row[b] != I:
                         self.errors.append(f"thread {mw} issues row {I} from buffer {b} holding row {self.buf_row[b]}")
+                    for c in range(self.nch):      # the issuing thread meets the later chunks' barriers inside its issue loop
+                        if c > 0:
+                            fc = self.full[b * self.nch + c]
+                            yield lambda fc=fc, fph=fph: fc.passed(fph)
+                        if self.tile_row[b * self.nch + c] != I:
+                            self.errors.append(f"thread {mw} issues chunk {c} of row {I} from a tile holding row {self.tile_row[b * self.nch + c]}")
                     self.issued_by.setdefault(I, set()).add(mw)
                     q = self.queues[mw]
                     q.append(("mma", I))
@@ -167,8 +178,9 @@ class Model:
             return False
         c = self.rng.choice(choices)
         if c == "tma":
-            b, _ = self.tma.pop(self.rng.randrange(len(self.tma)))
-            self.full[b].arrive()
+            t, row = self.tma.pop(self.rng.randrange(len(self.tma)))   # tiles land in any order
+            self.tile_row[t] = row
+            self.full[t].arrive()
         else:
             op = self.queues[c].pop(0)                            # per-thread order; no order across threads assumed
             if op[0] == "mma":
@@ -178,9 +190,9 @@ class Model:
         return True
 
 
-def run(mode, nblk, stages, segments, seed, freeze=True):
+def run(mode, nblk, stages, segments, seed, freeze=True, chunks=1):
     rng = random.Random(seed)
-    m = Model(mode, nblk, stages, segments, rng)
+    m = Model(mode, nblk, stages, segments, rng, chunks)
     agents = {"prod": m.producer(), "mma0": m.issuer(0), "mma1": m.issuer(1),
               "epi0": m.epilogue(0), "epi1": m.epilogue(1), "epi2": m.epilogue(2)}
     waiting = {k: None for k in agents}
@@ -277,3 +289,18 @@ def test_protocol_on_random_shapes_with_the_planner_rules():
         for mode in (0, 2):
             m, dead = run(mode, nblk, stages, segs, seed=case)
             assert dead is None and not m.errors, (mode, nblk, stages, n, h, x_tiles, grid, segs, dead, m.errors[:2])
+
+
+@pytest.mark.parametrize("nblk,stages,chunks,segments", [(16, 2, 3, [28]), (16, 2, 3, [1, 14, 2]), (16, 4, 2, [16]), (8, 4, 2, [15, 3]),
+                                                         (16, 2, 2, [2, 2, 2, 9]), (8, 2, 3, [1]), (16, 2, 3, [30, 1, 1]),
+                                                         (16, 3, 2, [40]), (8, 3, 2, [7, 9])])
+def test_chunk_barriers_are_live_and_safe(nblk, stages, chunks, segments):
+    """ConvKParams::chunk_bars (row-alternating issuers, stages * chunks <= 8): one landed-barrier per K-chunk tile, tiles
+    landing in any order; a chunk's MMAs must only ever be issued from a tile that holds that row's chunk, and nobody may be
+    lapped on a chunk barrier.  The later chunks' barriers are polled by the issuing warp only; with an odd ring depth a
+    buffer alternates between the warps and each polls them every second phase — still safe, because the phase in between
+    was met by the other warp earlier in turn order (the planner nevertheless keeps to even depths)."""
+    for seed in range(120):
+        m, dead = run(2, nblk, stages, segments, seed, chunks=chunks)
+        assert dead is None, (nblk, stages, chunks, segments, seed, dead)
+        assert not m.errors, (seed, m.errors[:3])
