@@ -81,6 +81,8 @@ class Conv3x3Desc(C.Structure):
         ("slice_stride", C.c_int64),
         ("f32_planar", C.c_int32),
         ("k_valid", C.c_int32),
+        ("out_lo", C.c_int32),
+        ("ob_lo_c0", C.c_int32),
     ]
 
 

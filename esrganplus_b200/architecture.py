@@ -134,6 +134,7 @@ class _GeneratorBase(_NativeWeights, nn.Module):
     def __getstate__(self):
         st = self.__dict__.copy()
         st["_engines"] = {}
+        st.pop("_precise_engines", None)
         return st
 
     def _engine_for(self, device: torch.device):
@@ -171,6 +172,23 @@ class _GeneratorBase(_NativeWeights, nn.Module):
         eng = self._engine_for(img.device)
         eng.sync_weights(dict(zip(names, plist)), self.weights_epoch)
         return eng.forward_u8(img, bgr)
+
+    def forward_fp32_parity(self, x: torch.Tensor) -> torch.Tensor:
+        """Not part of the reference surface: the eval-mode forward in SPLIT PRECISION (esrganplus_b200/precise.py) — every
+        value carried as two bf16 tensors, every conv as A_hi W_hi + A_lo W_hi + A_hi W_lo on the same tcgen05 kernels,
+        fp32 accumulation and fp32 residuals.  Matches the reference's fp32 arithmetic to ~1e-5 of the output's spread
+         at several times the cost of ``forward``.  No noise, no gradients."""
+        if not x.is_cuda:
+            raise RuntimeError("esrganplus_b200.RRDBNet runs on CUDA (sm_100a) only")
+        if self.training:
+            raise RuntimeError("forward_fp32_parity is an eval-mode path (call net.eval() first)")
+        from .precise import PreciseGenerator
+        engines = self.__dict__.setdefault("_precise_engines", {})
+        eng = engines.get(x.device)
+        if eng is None:
+            eng = engines[x.device] = PreciseGenerator(self, x.device)
+        with torch.no_grad():
+            return eng.forward(self, x.contiguous())
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if not x.is_cuda:

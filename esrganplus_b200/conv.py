@@ -111,6 +111,7 @@ class ConvCall:
     slice_stride: int = 0
     f32_planar: int = 0                      # fp32 r1 / r2 / out_f32 are [n,h,c/4,w,4] in memory (include/esrp.h)
     k_valid: int = 0                         # input channels that carry non-zero weights (0 = all)
+    ob_lo_c0: int = -1                       # >= 0: also store bf16(v - bf16(v)) at this channel offset of out_bf16 (tile kernel)
     _keep: list = field(default_factory=list, repr=False)
 
     def desc(self) -> Conv3x3Desc:
@@ -171,6 +172,7 @@ class ConvCall:
         d.slices, d.slice_stride = self.slices, self.slice_stride
         d.f32_planar = self.f32_planar
         d.k_valid = self.k_valid
+        d.out_lo, d.ob_lo_c0 = (1, self.ob_lo_c0) if self.ob_lo_c0 >= 0 else (0, 0)
         return d
 
     def launch(self) -> None:

@@ -457,6 +457,22 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
               }
               op[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
+            if (p.out_lo) {  // split precision: what the bf16 rounding above dropped, as a second bf16 tensor slice
+              uint4* ol = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.ob_ctotal + p.ob_lo_c0 + ch0);
+#pragma unroll
+              for (int i = 0; i < GC / 8; ++i) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float a = v[8 * i + 2 * j], b = v[8 * i + 2 * j + 1];
+                  const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+                  const float2 hf = __bfloat1622float2(h2);
+                  const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+                  pk[j] = *reinterpret_cast<const uint32_t*>(&l2);
+                }
+                ol[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
           }
           if (p.out_f32) {
             float4* op = reinterpret_cast<float4*>(p.out_f32 + pix * p.of_ctotal + p.of_c0 + ch0);

@@ -62,6 +62,7 @@ struct ConvKParams {
   int last_half;           // row kernel (row_alt): only the first kc/2 channels of the last chunk carry weights
   int row_alt;             // row kernel: the two MMA issuers alternate whole rows instead of splitting the taps of every row
   int no_quad;             // row kernel: store bf16 outputs pixel by pixel (timing experiments: ESRP_NO_QUAD)
+  int out_lo, ob_lo_c0;    // tile kernel: also store bf16(v - bf16(v)) at channel ob_lo_c0 of out_bf16 (esrp_conv3x3_t::out_lo)
   int chunk_bars;          // row kernel (row_alt, even ring depth, stages * num_chunks <= 8): one "data landed" barrier per K-chunk
                            // tile instead of one per row, so the MMAs of chunk c start when chunk c is there
   int dbg;           // timing experiments only (ESRP_DBG_*): results are wrong when non-zero

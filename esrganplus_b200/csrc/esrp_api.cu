@@ -140,6 +140,8 @@ int plan_conv(const esrp_conv3x3_t& d, ConvLaunch* out) {
   if (!d.src[0] || !d.w_packed) return set_error("conv3x3: null src/weights");
   if (d.cout < 1 || d.cout > d.bn) return set_error("conv3x3: cout=%d vs bn=%d", d.cout, d.bn);
   if (d.act < 0 || d.act > 2) return set_error("conv3x3: act=%d (0 none, 1 LeakyReLU(0.2), 2 ReLU)", d.act);
+  if (d.out_lo && (d.w_layout != ESRP_LAYOUT_TILE || !d.out_bf16 || d.ob_lo_c0 < 0 || (d.ob_lo_c0 % 8) || d.ob_lo_c0 + d.cout > d.ob_ctotal || d.slices > 1))
+    return set_error("conv3x3: out_lo needs ESRP_LAYOUT_TILE weights, an out_bf16 tensor and an 8-aligned ob_lo_c0 inside it");
   for (int i = 0; i < d.num_chunks; ++i) {
     int s_ = d.chunk_src[i];
     if (s_ < 0 || s_ > 1 || !d.src[s_]) return set_error("conv3x3: chunk %d reads missing src %d", i, s_);

@@ -27,6 +27,7 @@ void copy_common(const esrp_conv3x3_t& d, ConvKParams* pp) {
   p.nsl = d.slices > 1 ? d.slices : 1;
   p.sl_stride = d.slices > 1 ? d.slice_stride : 0;
   p.f32_planar = d.f32_planar;
+  p.out_lo = d.out_lo; p.ob_lo_c0 = d.ob_lo_c0;
   p.trace = static_cast<long long*>(d.trace);
   p.dbg = d.variant & 0x1F00;
   p.mask_out = static_cast<unsigned short*>(d.mask_out); p.mo_ctotal = d.mask_out_ctotal; p.mo_c0 = d.mask_out_c0;

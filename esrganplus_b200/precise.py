@@ -1,0 +1,185 @@
+"""fp32-parity forward of ``RRDBNet`` on the bf16 tensor pipe (split precision).
+
+The fast path (engine.py) multiplies bf16 operands: ~53 dB PSNR against the reference's fp32 arithmetic (DESIGN.md section
+4.3).  This module is the ACCURACY mode the same kernels offer: every fp32 value v is carried as two bf16 tensors,
+hi = bf16(v) and lo = bf16(v - hi) (16 mantissa bits together), and every convolution runs its K loop three times over
+(A_hi W_hi + A_lo W_hi + A_hi W_lo) in ONE launch: the activations [hi | lo] are extra channel ranges of the same NHWC
+tensor, the weights [W_hi | W_hi | W_lo] extra input channels of one packed tile, so the kernel sees an ordinary conv with
+three times the K chunks and accumulates all of it in fp32 in tensor memory.  The epilogue stores both halves of its result
+(``esrp_conv3x3_t::out_lo``).  Residual adds (conv1x1 / x2 / trunk / RRDB, block.py:262-268,291) take fp32 tensors.
+
+Cost: 3x the MMAs on the weight-streaming tile kernel (the row kernel keeps its weights resident and has no room for
+nine-chunk sets), one C-ABI call per conv from Python.  It is meant for validation and for callers who need the reference's
+numerics, not for throughput.  Eval mode only (no noise, no gradients).
+
+Reference arithmetic: codes/models/modules/architecture.py:47-78, block.py:232-291 — the same graph as engine.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from . import conv as K
+
+KC = 32   # every logical input range (3 -> 32 padded image channels, 64 trunk channels, 32 growth channels) is a multiple
+
+
+def _split(t: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    hi = t.to(torch.bfloat16)
+    return hi, (t - hi.float()).to(torch.bfloat16)
+
+
+class _Conv:
+    """One 3x3 conv of the network in split precision: packed [W_hi | W_hi | W_lo] tiles per output slice + bias."""
+
+    def __init__(self, w: torch.Tensor, b: Optional[torch.Tensor], cin_pad: int):
+        cout, cin = w.shape[0], w.shape[1]
+        if w.shape[2] == 1:   # the bias-free 1x1 of block.py:244 as a 3x3 with one tap
+            w3 = torch.zeros((cout, cin, 3, 3), dtype=torch.float32, device=w.device)
+            w3[:, :, 1, 1] = w[:, :, 0, 0]
+            w = w3
+        if cin_pad > cin:
+            w = torch.cat([w, torch.zeros((cout, cin_pad - cin, 3, 3), dtype=w.dtype, device=w.device)], 1)
+        hi = w.to(torch.bfloat16).float()
+        lo = (w - hi).to(torch.bfloat16).float()
+        wcat = torch.cat([hi, hi, lo], 1).contiguous()
+        self.cin, self.cout = cin_pad, cout
+        self.bn = 16 if cout <= 16 else (32 if cout <= 32 else 64)
+        lc0 = list(range(0, 3 * cin_pad, KC))
+        self.slices = []
+        for r0 in range(0, cout, self.bn):
+            rows = min(self.bn, cout - r0)
+            wp = K.pack_conv3x3_weights(wcat, KC, self.bn, lc0, row0=r0, rows=rows, layout=_lib.LAYOUT_TILE)
+            bias = torch.zeros(self.bn, dtype=torch.float32, device=w.device)
+            if b is not None:
+                bias[:rows] = b[r0:r0 + rows]
+            self.slices.append((r0, rows, wp, bias))
+
+
+class PreciseGenerator:
+    """Launch logic of one RRDBNet / RRDB_Net module on one device."""
+
+    def __init__(self, module, device: torch.device):
+        self.lib = _lib.load()
+        self.device = device
+        self.cfg = dict(module.cfg)
+        self.epoch = None
+        self.convs: Dict[str, _Conv] = {}
+
+    # ---- weights -------------------------------------------------------------------------------
+    def sync(self, module) -> None:
+        ep = (module.weights_epoch, tuple((p.data_ptr(), p._version) for p in module.parameters()))
+        if ep == self.epoch:
+            return
+        sd = {k: v.detach().float() for k, v in module.state_dict().items()}
+        c = self.cfg
+        nf, nb, n_up = c["nf"], c["nb"], {1: 0, 2: 1, 4: 2}[c["upscale"]]
+        in_pad = (c["in_nc"] + KC - 1) // KC * KC
+        cv: Dict[str, _Conv] = {}
+        cv["fea"] = _Conv(sd["model.0.weight"], sd["model.0.bias"], in_pad)
+        for i in range(nb):
+            for r in (1, 2, 3):
+                pre = f"model.1.sub.{i}.RDB{r}."
+                cv[pre + "conv1x1"] = _Conv(sd[pre + "conv1x1.weight"], None, nf)
+                for k in range(1, 6):
+                    cv[pre + f"conv{k}"] = _Conv(sd[pre + f"conv{k}.0.weight"], sd[pre + f"conv{k}.0.bias"], nf + (k - 1) * c["gc"])
+        cv["trunk"] = _Conv(sd[f"model.1.sub.{nb}.weight"], sd[f"model.1.sub.{nb}.bias"], nf)
+        idx = 3
+        for u in range(n_up):   # block.py:315-322: [Upsample, conv, act] flattened into the top-level Sequential
+            cv[f"up{u}"] = _Conv(sd[f"model.{idx}.weight"], sd[f"model.{idx}.bias"], nf)
+            idx += 3
+        cv["hr0"] = _Conv(sd[f"model.{2 + 3 * n_up}.weight"], sd[f"model.{2 + 3 * n_up}.bias"], nf)   # HR_conv0 (+ act), architecture.py:70
+        cv["hr1"] = _Conv(sd[f"model.{4 + 3 * n_up}.weight"], sd[f"model.{4 + 3 * n_up}.bias"], nf)   # HR_conv1, :71
+        self.convs, self.epoch, self.n_up = cv, ep, n_up
+
+    # ---- one conv ------------------------------------------------------------------------------
+    def _conv(self, cv: _Conv, n: int, h: int, w: int, srcs: List[torch.Tensor], segs: List[Tuple[int, int, int, int]], act: int,
+              out: Optional[torch.Tensor] = None, out_hi: int = 0, out_lo: int = 0, out_f32: Optional[torch.Tensor] = None,
+              of_c0: int = 0, s0: float = 1.0, r1: Optional[torch.Tensor] = None, r1_c0: int = 0, r2: Optional[torch.Tensor] = None,
+              r2_c0: int = 0, s2: float = 1.0, out_nchw: Optional[torch.Tensor] = None) -> None:
+        """segs: the conv's input channels in weight order as (source index, hi offset, lo offset, channels)."""
+        assert sum(s[3] for s in segs) == cv.cin, (segs, cv.cin)
+        hi_chunks = [(si, hc + c) for si, hc, _lc, nch in segs for c in range(0, nch, KC)]
+        lo_chunks = [(si, lc + c) for si, _hc, lc, nch in segs for c in range(0, nch, KC)]
+        chunks = hi_chunks + lo_chunks + hi_chunks            # x [W_hi | W_hi | W_lo]
+        for r0, rows, wp, bias in cv.slices:
+            call = K.ConvCall(n=n, h=h, w=w, srcs=srcs, kc=KC, chunks=chunks, bn=cv.bn, cout=rows, w_packed=wp, w_layout=_lib.LAYOUT_TILE,
+                              bias=bias, act=act, s0=s0)
+            if r1 is not None:
+                call.r1, call.r1_c0, call.s1 = r1, r1_c0 + r0, 1.0
+            if r2 is not None:
+                call.r2, call.r2_c0, call.s2 = r2, r2_c0 + r0, s2
+            if out is not None:
+                call.out_bf16, call.ob_c0, call.ob_lo_c0 = out, out_hi + r0, out_lo + r0
+            if out_f32 is not None:
+                call.out_f32, call.of_c0 = out_f32, of_c0 + r0
+            if out_nchw is not None:
+                call.out_nchw = out_nchw
+            call.launch()
+
+    # ---- the network ---------------------------------------------------------------------------
+    def forward(self, module, x: torch.Tensor) -> torch.Tensor:
+        if x.dim() != 4 or x.dtype != torch.float32 or x.device != self.device:
+            raise RuntimeError("fp32-parity forward expects an fp32 NCHW CUDA tensor")
+        self.sync(module)
+        c = self.cfg
+        nf, gc, nb = c["nf"], c["gc"], c["nb"]
+        n, cin, h, w = x.shape
+        dev = self.device
+        bf, f32 = torch.bfloat16, torch.float32
+        in_pad = (cin + KC - 1) // KC * KC
+        # image as [hi | lo] NHWC, channels padded to 32
+        xh, xl = _split(x.permute(0, 2, 3, 1).contiguous())
+        x2 = torch.zeros((n, h, w, 2 * in_pad), dtype=bf, device=dev)
+        x2[..., :cin] = xh
+        x2[..., in_pad:in_pad + cin] = xl
+        T = [torch.empty((n, h, w, 2 * nf), dtype=bf, device=dev) for _ in range(3)]       # [hi nf | lo nf]
+        Tf = [torch.empty((n, h, w, nf), dtype=f32, device=dev) for _ in range(3)]
+        fea2 = torch.empty((n, h, w, 2 * nf), dtype=bf, device=dev)
+        feaf = torch.empty((n, h, w, nf), dtype=f32, device=dev)
+        G = torch.zeros((n, h, w, 8 * gc), dtype=bf, device=dev)                            # [hi 4gc | lo 4gc]
+        c11 = torch.empty((n, h, w, gc), dtype=f32, device=dev)
+        x2f = torch.empty((n, h, w, gc), dtype=f32, device=dev)
+        cv = self.convs
+        self._conv(cv["fea"], n, h, w, [x2], [(0, 0, in_pad, in_pad)], 0, out=fea2, out_hi=0, out_lo=nf, out_f32=feaf)
+        cur, curf = fea2, feaf
+        for i in range(nb):
+            rrf = curf
+            for r in (1, 2, 3):
+                pre = f"model.1.sub.{i}.RDB{r}."
+                slot = next(s for s in range(3) if Tf[s] is not curf and Tf[s] is not rrf)
+                tseg = (0, 0, nf, nf)
+                gseg = lambda k: [(1, 0, 4 * gc, (k - 1) * gc)] if k > 1 else []
+                srcs = lambda k: [cur, G] if k > 1 else [cur]
+                # x1 = lrelu(conv1(x))                                             block.py:261
+                self._conv(cv[pre + "conv1"], n, h, w, srcs(1), [tseg], 1, out=G, out_hi=0, out_lo=4 * gc)
+                # x2 = lrelu(conv2([x, x1])) + conv1x1(x)                          block.py:262-263
+                self._conv(cv[pre + "conv1x1"], n, h, w, [cur], [tseg], 0, out_f32=c11)
+                self._conv(cv[pre + "conv2"], n, h, w, srcs(2), [tseg] + gseg(2), 1, out=G, out_hi=gc, out_lo=5 * gc, out_f32=x2f, r1=c11)
+                self._conv(cv[pre + "conv3"], n, h, w, srcs(3), [tseg] + gseg(3), 1, out=G, out_hi=2 * gc, out_lo=6 * gc)
+                # x4 = lrelu(conv4(..)) + x2                                        block.py:265-266
+                self._conv(cv[pre + "conv4"], n, h, w, srcs(4), [tseg] + gseg(4), 1, out=G, out_hi=3 * gc, out_lo=7 * gc, r1=x2f)
+                # out = 0.2 * conv5(..) + x  (eval: GaussianNoise is the identity)  block.py:267-268; RRDB: * 0.2 + x, :291
+                self._conv(cv[pre + "conv5"], n, h, w, srcs(5), [tseg] + gseg(5), 0, out=T[slot], out_hi=0, out_lo=nf, out_f32=Tf[slot],
+                           s0=0.2, r1=curf, r2=rrf if r == 3 else None, s2=0.2)
+                cur, curf = T[slot], Tf[slot]
+        # LR_conv + shortcut (architecture.py:58,73)
+        u = torch.empty((n, h, w, 2 * nf), dtype=bf, device=dev)
+        self._conv(cv["trunk"], n, h, w, [cur], [(0, 0, nf, nf)], 0, out=u, out_hi=0, out_lo=nf, r1=feaf)
+        feat, hh, ww = u, h, w
+        st = torch.cuda.current_stream(dev).cuda_stream
+        for k in range(self.n_up):   # nearest x2 -> conv -> lrelu (block.py:315-322); [hi | lo] travel together
+            up = torch.empty((n, 2 * hh, 2 * ww, 2 * nf), dtype=bf, device=dev)
+            _lib.check(self.lib.esrp_upsample2x_nhwc_bf16(feat.data_ptr(), up.data_ptr(), n, hh, ww, 2 * nf, st), "esrp_upsample2x_nhwc_bf16")
+            hh, ww = 2 * hh, 2 * ww
+            o = torch.empty((n, hh, ww, 2 * nf), dtype=bf, device=dev)
+            self._conv(cv[f"up{k}"], n, hh, ww, [up], [(0, 0, nf, nf)], 1, out=o, out_hi=0, out_lo=nf)
+            feat = o
+        o = torch.empty((n, hh, ww, 2 * nf), dtype=bf, device=dev)
+        self._conv(cv["hr0"], n, hh, ww, [feat], [(0, 0, nf, nf)], 1, out=o, out_hi=0, out_lo=nf)
+        y = torch.empty((n, c["out_nc"], hh, ww), dtype=f32, device=dev)
+        self._conv(cv["hr1"], n, hh, ww, [o], [(0, 0, nf, nf)], 0, out_nchw=y)
+        return y

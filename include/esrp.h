@@ -136,6 +136,13 @@ typedef struct esrp_conv3x3 {
    * (a dense-block conv whose Cin is not a multiple of kc, block.py:253-257: conv2 96, conv4 160).
    * The kernel may skip MMAs over the zero-weight tail; results are unchanged. */
   int32_t k_valid;
+  /* ---- split-precision output (optional; ESRP_LAYOUT_TILE only) ----
+   * out_lo = 1: besides hi = bf16(v) at ob_c0 the kernel stores lo = bf16(v - hi) at ob_lo_c0 of the SAME out_bf16 tensor.
+   * A caller that feeds [hi | lo] activations and [W_hi | W_hi | W_lo] weights through three chunk groups
+   * (A_hi, A_lo, A_hi) gets products accurate to ~16 mantissa bits out of the bf16 tensor pipe: the fp32-parity mode of
+   * esrganplus_b200/precise.py. */
+  int32_t out_lo;
+  int32_t ob_lo_c0;
 } esrp_conv3x3_t;
 
 const char* esrp_last_error(void);

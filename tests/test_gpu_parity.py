@@ -369,6 +369,70 @@ def test_rrdbnet_nb23_matches_reference_fixture(cuda_dev, golden_dir):
     _net_close(net(torch.from_numpy(g["x_ragged"]).to(cuda_dev)).cpu(), torch.from_numpy(g["y_ragged"]), "nb23 ragged")
 
 
+def test_conv3x3_split_precision_output(cuda_dev):
+    """esrp_conv3x3_t::out_lo: hi = bf16(v) and lo = bf16(v - hi) land in two channel ranges of one tensor; hi + lo
+    reproduces the fp32 result to 2^-16 relative, and a conv fed [A_hi | A_lo] x [W_hi | W_hi | W_lo] (three chunk groups)
+    reproduces the fp32 conv of the UNROUNDED operands to ~1e-5 (bf16 operands alone: ~4e-3)."""
+    n, h, w, cin, cout = 2, 20, 27, 64, 32
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    bias = torch.randn(cout, generator=g)
+    ref = F.conv2d(x.double(), wt.double(), bias.double(), padding=1).float()
+    xh = x.to(torch.bfloat16)
+    xl = (x - xh.float()).to(torch.bfloat16)
+    a = torch.cat([xh, xl], 1).permute(0, 2, 3, 1).contiguous().to(cuda_dev)                      # [n,h,w, hi 64 | lo 64]
+    wh = wt.to(torch.bfloat16).float()
+    wl = (wt - wh).to(torch.bfloat16).float()
+    wcat = torch.cat([wh, wh, wl], 1).to(cuda_dev)
+    wp = K.pack_conv3x3_weights(wcat, 32, 32, list(range(0, 3 * cin, 32)), layout=_lib.LAYOUT_TILE)
+    chunks = [(0, c) for c in (0, 32)] + [(0, c) for c in (64, 96)] + [(0, c) for c in (0, 32)]
+    out = torch.zeros((n, h, w, 2 * cout), dtype=torch.bfloat16, device=cuda_dev)
+    of = torch.zeros((n, h, w, cout), device=cuda_dev)
+    K.ConvCall(n=n, h=h, w=w, srcs=[a], kc=32, chunks=chunks, bn=32, cout=cout, w_packed=wp, w_layout=_lib.LAYOUT_TILE,
+               bias=bias.to(cuda_dev), out_bf16=out, ob_c0=0, ob_lo_c0=cout, out_f32=of).launch()
+    y32 = of.permute(0, 3, 1, 2).cpu()
+    hi, lo = out[..., :cout].float(), out[..., cout:].float()
+    assert torch.equal(hi, of.to(torch.bfloat16).float())
+    assert torch.equal(lo, (of - hi).to(torch.bfloat16).float())
+    scale = ref.abs().max().item()
+    err_split = (y32 - ref).abs().max().item() / scale
+    err_bf16 = (F.conv2d(xh.float(), wh, bias, padding=1) - ref).abs().max().item() / scale
+    print(f"split-precision conv: max err {err_split:.2e} of max|ref| (bf16 operands: {err_bf16:.2e})")
+    assert err_split <= 3e-5 and err_bf16 >= 20 * err_split
+    # out_lo is a tile-kernel feature: the row layout rejects it
+    wr = K.pack_conv3x3_weights(wcat, 32, 32, list(range(0, 3 * cin, 32)), layout=_lib.LAYOUT_ROW)
+    with pytest.raises(RuntimeError):
+        K.ConvCall(n=n, h=h, w=w, srcs=[a], kc=32, chunks=chunks[:3], bn=32, cout=cout, w_packed=wr, w_layout=_lib.LAYOUT_ROW,
+                   out_bf16=out, ob_lo_c0=cout).launch()
+
+
+@pytest.mark.parametrize("cls", [E.RRDBNet, E.RRDB_Net])
+def test_fp32_parity_mode_matches_reference_fixtures(cuda_dev, golden_dir, cls):
+    """forward_fp32_parity (esrganplus_b200/precise.py, split precision on the same tcgen05 kernels) against outputs of the
+    reference itself.  Stated tolerance: max|d| <= 2e-4 std(ref) and PSNR >= 90 dB on the clamped image — three orders of
+    magnitude inside the fast path's 6e-2 / 48 dB, and below the 8-bit quantisation step by 50 dB."""
+    g = _golden(golden_dir, "rrdbnet_c1_nb1_nf32.npz")
+    net = _make(cls, O.synth_state_dict_g(3, 3, 32, 1, seed=21), 32, 1, cuda_dev)
+    cases = [("config 1", net, g["x"], g["y"])]
+    if cls is E.RRDBNet:
+        g23 = _golden(golden_dir, "rrdbnet_nb23_nf64.npz")
+        net23 = _make(cls, O.synth_state_dict_g(3, 3, 64, 23, seed=31), 64, 23, cuda_dev)
+        cases += [("nb23 24x24", net23, g23["x24"], g23["y24"]), ("nb23 ragged 2x19x37", net23, g23["x_ragged"], g23["y_ragged"])]
+    for what, m, x, yref in cases:
+        ref = torch.from_numpy(yref)
+        y = m.forward_fp32_parity(torch.from_numpy(x).to(cuda_dev)).cpu()
+        rel = (y - ref).abs().max().item() / ref.std().item()
+        psnr = O.psnr_255(y, ref)
+        fast = m(torch.from_numpy(x).to(cuda_dev)).cpu()
+        rel_fast = (fast - ref).abs().max().item() / ref.std().item()
+        print(f"fp32-parity mode, {what}: max|d|/std {rel:.2e}, PSNR {psnr:.1f} dB (fast path: {rel_fast:.2e}, {O.psnr_255(fast, ref):.1f} dB)")
+        assert y.shape == ref.shape and rel <= 2e-4 and psnr >= 90.0, (what, rel, psnr)
+    net.train()
+    with pytest.raises(RuntimeError):
+        net.forward_fp32_parity(torch.from_numpy(g["x"]).to(cuda_dev))
+
+
 def test_weight_cache_follows_parameter_updates(cuda_dev):
     sd_a = O.synth_state_dict_g(3, 3, 32, 1, seed=1)
     sd_b = O.synth_state_dict_g(3, 3, 32, 1, seed=2)
