@@ -29,6 +29,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -383,7 +384,7 @@ def main_ours(args):
     except Exception as e:
         e2e_u8 = {"error": f"{type(e).__name__}: {e}"[:300]}
     # ---- secondary inference legs -------------------------------------------------------------------------------
-    chain_leg = tiled_leg = lib_leg = None
+    chain_leg = tiled_leg = lib_leg = parity_leg = None
     eng = net._engines[dev]
     launches_plain = eng.num_launches
     if not args.no_extras:
@@ -421,6 +422,22 @@ def main_ours(args):
                          "workload": "one 512x512 LR image -> 2048x2048, 16 crops of 128x128 sharded round-robin (config 3)"}
         except Exception as e:
             tiled_leg = {"error": f"{type(e).__name__}: {e}"[:300]}
+        try:    # the accuracy mode (esrganplus_b200/precise.py): same workload, split precision on the tile kernel
+            with torch.no_grad():
+                yp = net.forward_fp32_parity(x_dev)
+                yf = net(x_dev)
+                torch.cuda.synchronize()
+                dev_db = 10.0 * math.log10(1.0 / max(1e-30, float(((yp.clamp(0, 1) - yf.clamp(0, 1)) ** 2).mean())))
+                del yp, yf
+                ms_p = timed(lambda: net.forward_fp32_parity(x_dev), 3)
+            parity_leg = {"value": BATCH * OUT_MP_PER_TILE * world / (ms_p / 3 * 1e-3), "unit": "MP/s", "ms_per_step": ms_p / 3,
+                          "fast_path_psnr_against_it_db": dev_db,
+                          "note": "RRDBNet.forward_fp32_parity: every value as two bf16 tensors, A_hi W_hi + A_lo W_hi + A_hi W_lo per conv, "
+                                  "fp32 accumulation and residuals; 107 dB against the reference fixtures (tests), 3 timed steps"}
+            net.__dict__.pop("_precise_engines", None)
+            torch.cuda.empty_cache()
+        except Exception as e:
+            parity_leg = {"error": f"{type(e).__name__}: {e}"[:300]}
         if world == 1:
             try:
                 lib_leg = gpu_library_baseline(torch, dev, sd, x_dev)
@@ -505,6 +522,7 @@ def main_ours(args):
             "chain": chain_leg,
             "tiled": tiled_leg,
             "gpu_library_baseline": lib_leg,
+            "fp32_parity": parity_leg,
             "attempts": 1,
             "train": train,
             "train_strong": train_strong,
