@@ -428,6 +428,15 @@ def test_fp32_parity_mode_matches_reference_fixtures(cuda_dev, golden_dir, cls):
         rel_fast = (fast - ref).abs().max().item() / ref.std().item()
         print(f"fp32-parity mode, {what}: max|d|/std {rel:.2e}, PSNR {psnr:.1f} dB (fast path: {rel_fast:.2e}, {O.psnr_255(fast, ref):.1f} dB)")
         assert y.shape == ref.shape and rel <= 2e-4 and psnr >= 90.0, (what, rel, psnr)
+    # test_image/test.py:31-40 around the parity mode: the reference's 8-bit output image, to within one level in < 1 % of the
+    # pixels (the fast path needs +-2 levels and up to 25 %: test_rrdbnet_config1_matches_reference_fixture)
+    img = g["img_u8"] * 1.0 / 255
+    t = torch.from_numpy(np.transpose(img[:, :, [2, 1, 0]], (2, 0, 1))).float().unsqueeze(0).to(cuda_dev)
+    out = net.forward_fp32_parity(t).data.squeeze().float().cpu().clamp_(0, 1).numpy()
+    out = (np.transpose(out[[2, 1, 0], :, :], (1, 2, 0)) * 255.0).round().astype("uint8")
+    diff = np.abs(out.astype(int) - g["out_u8"].astype(int))
+    print(f"fp32-parity mode, 8-bit image: max level difference {diff.max()}, {100.0 * (diff > 0).mean():.3f} % of the pixels differ")
+    assert diff.max() <= 1 and (diff > 0).mean() < 0.01, (diff.max(), (diff > 0).mean())
     net.train()
     with pytest.raises(RuntimeError):
         net.forward_fp32_parity(torch.from_numpy(g["x"]).to(cuda_dev))
