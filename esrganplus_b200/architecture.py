@@ -160,13 +160,24 @@ class _GeneratorBase(_NativeWeights, nn.Module):
                 rank = dist.get_rank(None if g is True else g)
         return (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._step + rank * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
 
-    def forward_uint8(self, img: torch.Tensor, bgr: bool = True) -> torch.Tensor:
+    def forward_uint8(self, img: torch.Tensor, bgr: bool = True, fp32_parity: bool = False) -> torch.Tensor:
         """Not part of the reference surface: 8-bit images in, 8-bit images out, with the host
         plumbing of test_image/test.py:31-40 (``/255``, BGR<->RGB, ``clamp_(0,1)``, ``(x*255).round()``) done on the
         device — a 4x smaller device->host copy and no numpy pass.  img: uint8 [n,h,w,in_nc] CUDA tensor (cv2 order when
-        `bgr`); always the eval-mode network, no gradient."""
+        `bgr`); always the eval-mode network, no gradient.  `fp32_parity=True` runs the split-precision forward
+        (forward_fp32_parity) inside the same plumbing."""
         if not img.is_cuda:
             raise RuntimeError("esrganplus_b200.RRDBNet runs on CUDA (sm_100a) only")
+        if fp32_parity:
+            # the same plumbing around the split-precision forward (the result then equals the reference's 8-bit image);
+            # torch ops: this is the accuracy mode, not the fast one
+            if img.dim() != 4 or img.dtype != torch.uint8:
+                raise RuntimeError("forward_uint8 expects a uint8 [n,h,w,c] tensor")
+            x = img.flip(-1) if bgr else img
+            x = (x.permute(0, 3, 1, 2).to(torch.float64) * 1.0 / 255).float().contiguous()   # test_image/test.py:31-33
+            y = self.forward_fp32_parity(x).clamp_(0, 1)                                      # :37
+            y = (y.permute(0, 2, 3, 1) * 255.0).round().to(torch.uint8)                       # :38-39
+            return (y.flip(-1) if bgr else y).contiguous()
         from .discriminator import _named_params
         names, plist = _named_params(self)
         eng = self._engine_for(img.device)

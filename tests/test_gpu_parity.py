@@ -437,6 +437,10 @@ def test_fp32_parity_mode_matches_reference_fixtures(cuda_dev, golden_dir, cls):
     diff = np.abs(out.astype(int) - g["out_u8"].astype(int))
     print(f"fp32-parity mode, 8-bit image: max level difference {diff.max()}, {100.0 * (diff > 0).mean():.3f} % of the pixels differ")
     assert diff.max() <= 1 and (diff > 0).mean() < 0.01, (diff.max(), (diff > 0).mean())
+    if cls is E.RRDBNet:   # the same through forward_uint8(fp32_parity=True): plumbing on the device
+        dev_out = net.forward_uint8(torch.from_numpy(g["img_u8"]).unsqueeze(0).to(cuda_dev), fp32_parity=True).cpu().numpy()[0]
+        d2 = np.abs(dev_out.astype(int) - g["out_u8"].astype(int))
+        assert dev_out.shape == g["out_u8"].shape and d2.max() <= 1 and (d2 > 0).mean() < 0.01, (d2.max(), (d2 > 0).mean())
     net.train()
     with pytest.raises(RuntimeError):
         net.forward_fp32_parity(torch.from_numpy(g["x"]).to(cuda_dev))
