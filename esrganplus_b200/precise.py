@@ -68,6 +68,8 @@ class PreciseGenerator:
         self.cfg = dict(module.cfg)
         self.epoch = None
         self.convs: Dict[str, _Conv] = {}
+        self.plans: Dict[tuple, dict] = {}
+        self._rec: Optional[list] = None
 
     # ---- weights -------------------------------------------------------------------------------
     def sync(self, module) -> None:
@@ -118,24 +120,41 @@ class PreciseGenerator:
                 call.out_f32, call.of_c0 = out_f32, of_c0 + r0
             if out_nchw is not None:
                 call.out_nchw = out_nchw
-            call.launch()
+            d = call.desc()
+            self._rec.append((self.lib.esrp_conv3x3_nhwc, (C.byref(d),), d, "esrp_conv3x3_nhwc"))
 
     # ---- the network ---------------------------------------------------------------------------
     def forward(self, module, x: torch.Tensor) -> torch.Tensor:
         if x.dim() != 4 or x.dtype != torch.float32 or x.device != self.device:
             raise RuntimeError("fp32-parity forward expects an fp32 NCHW CUDA tensor")
         self.sync(module)
+        n, cin, h, w = x.shape
+        in_pad = (cin + KC - 1) // KC * KC
+        plan = self.plans.get((n, h, w))
+        if plan is None or plan["epoch"] is not self.epoch:
+            # launch plan of this shape: every buffer and descriptor is built once (the packed weights of this epoch are baked
+            # into the descriptors), later calls replay ~560 C-ABI calls
+            self.plans.clear()
+            plan = self.plans[(n, h, w)] = self._build(n, cin, h, w)
+        # image as [hi | lo] NHWC, channels padded to 32
+        xh, xl = _split(x.permute(0, 2, 3, 1))
+        plan["x2"][..., :cin] = xh
+        plan["x2"][..., in_pad:in_pad + cin] = xl
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        for fn, args, _keep, what in plan["calls"]:
+            rc = fn(*args, st)
+            if rc != 0:
+                _lib.check(rc, what)
+        return plan["y"].clone()
+
+    def _build(self, n: int, cin: int, h: int, w: int) -> dict:
         c = self.cfg
         nf, gc, nb = c["nf"], c["gc"], c["nb"]
-        n, cin, h, w = x.shape
         dev = self.device
         bf, f32 = torch.bfloat16, torch.float32
         in_pad = (cin + KC - 1) // KC * KC
-        # image as [hi | lo] NHWC, channels padded to 32
-        xh, xl = _split(x.permute(0, 2, 3, 1).contiguous())
+        self._rec = []
         x2 = torch.zeros((n, h, w, 2 * in_pad), dtype=bf, device=dev)
-        x2[..., :cin] = xh
-        x2[..., in_pad:in_pad + cin] = xl
         T = [torch.empty((n, h, w, 2 * nf), dtype=bf, device=dev) for _ in range(3)]       # [hi nf | lo nf]
         Tf = [torch.empty((n, h, w, nf), dtype=f32, device=dev) for _ in range(3)]
         fea2 = torch.empty((n, h, w, 2 * nf), dtype=bf, device=dev)
@@ -170,16 +189,20 @@ class PreciseGenerator:
         u = torch.empty((n, h, w, 2 * nf), dtype=bf, device=dev)
         self._conv(cv["trunk"], n, h, w, [cur], [(0, 0, nf, nf)], 0, out=u, out_hi=0, out_lo=nf, r1=feaf)
         feat, hh, ww = u, h, w
-        st = torch.cuda.current_stream(dev).cuda_stream
+        keep = [x2, T, Tf, fea2, feaf, G, c11, x2f, u]
         for k in range(self.n_up):   # nearest x2 -> conv -> lrelu (block.py:315-322); [hi | lo] travel together
             up = torch.empty((n, 2 * hh, 2 * ww, 2 * nf), dtype=bf, device=dev)
-            _lib.check(self.lib.esrp_upsample2x_nhwc_bf16(feat.data_ptr(), up.data_ptr(), n, hh, ww, 2 * nf, st), "esrp_upsample2x_nhwc_bf16")
+            self._rec.append((self.lib.esrp_upsample2x_nhwc_bf16, (feat.data_ptr(), up.data_ptr(), n, hh, ww, 2 * nf), None,
+                              "esrp_upsample2x_nhwc_bf16"))
+            keep.append(up)
             hh, ww = 2 * hh, 2 * ww
             o = torch.empty((n, hh, ww, 2 * nf), dtype=bf, device=dev)
             self._conv(cv[f"up{k}"], n, hh, ww, [up], [(0, 0, nf, nf)], 1, out=o, out_hi=0, out_lo=nf)
+            keep.append(o)
             feat = o
         o = torch.empty((n, hh, ww, 2 * nf), dtype=bf, device=dev)
         self._conv(cv["hr0"], n, hh, ww, [feat], [(0, 0, nf, nf)], 1, out=o, out_hi=0, out_lo=nf)
         y = torch.empty((n, c["out_nc"], hh, ww), dtype=f32, device=dev)
         self._conv(cv["hr1"], n, hh, ww, [o], [(0, 0, nf, nf)], 0, out_nchw=y)
-        return y
+        calls, self._rec = self._rec, None
+        return {"calls": calls, "x2": x2, "y": y, "keep": keep + [o], "epoch": self.epoch}
