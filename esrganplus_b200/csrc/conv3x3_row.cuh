@@ -142,14 +142,23 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
   constexpr uint32_t LAYOUT = (KC == 64) ? 2u : 4u;
   constexpr uint32_t SBO = 8 * RB;
   constexpr uint32_t DESC_HI = (SBO >> 4) | (1u << 14) | (LAYOUT << 29);
-  constexpr int NBLK = (AUX || BN == 64) ? 8 : 16;         // ring of output-row blocks (power of two)
-  constexpr int AUX_COL0 = NBLK * BN;                      // conv1x1 blocks live behind the main ring
+  // Ring of output-row blocks.  BN <= 32 (SHADOW): R ring positions plus two SHADOW blocks behind them that stand in for
+  // positions 0 / 1 when the three-block accumulator window of an input row would straddle the end of the ring, so the
+  // window is ALWAYS one contiguous N = 3*BN accumulator (no second, narrower MMA per tap on 2 of every R rows: those cost
+  // 1.5x a plain row).  The rows at positions 0 / 1 then have their sum spread over two blocks (main: the contributions
+  // issued while the window was at the bottom of the ring, shadow: the ones issued from its top); the epilogue adds them.
+  // BN = 64: 8 blocks, power-of-two ring, windows that straddle the end are issued as two MMAs (512 columns leave no
+  // room for shadows without shrinking the ring to 6).
+  constexpr bool SHADOW = BN <= 32;
+  constexpr int NBLK = SHADOW ? (AUX ? 7 : 14) : 8;        // ring positions
+  constexpr int NMAIN = SHADOW ? NBLK + 2 : NBLK;          // main blocks incl. the two shadows
+  constexpr int AUX_COL0 = NMAIN * BN;                     // conv1x1 blocks live behind the main blocks
   constexpr int nb_rows = AUX ? 4 * BN : 3 * BN;
   constexpr int w_block_bytes = nb_rows * RB;
   constexpr int w_chunk_bytes = 3 * w_block_bytes;
   constexpr int GC = BN < 16 ? BN : 16;                    // output channels per epilogue round
   constexpr int ROUNDS = BN / GC;
-  static_assert(NBLK <= kMaxBlocks && (AUX ? 2 : 1) * NBLK * BN <= 512, "TMEM budget");
+  static_assert(NBLK <= kMaxBlocks && (NMAIN + (AUX ? NBLK : 0)) * BN <= 512, "TMEM budget");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -222,7 +231,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
   // every block starts zeroed: all MMAs accumulate
   if (warp < kRowEpiWarps) {  // lane quarter warp % 4, a third of the columns each
     const uint32_t la = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    for (int c = (warp >> 2) * 16; c < NBLK * BN; c += 16 * kRowWGs) tmem_st_zero_x16(la + c);
+    for (int c = (warp >> 2) * 16; c < NMAIN * BN; c += 16 * kRowWGs) tmem_st_zero_x16(la + c);
     tmem_st_wait();
   }
   tcgen05_fence_before();
@@ -232,7 +241,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
   ESRP_FINE_TRACE(if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[2 * 1024 + 1019] = clock64();)
   // ring position (block index) of output sequence number O: descending, so that the blocks of the output
   // rows r+1, r, r-1 an input row r accumulates into are adjacent with ascending columns (ky = 0, 1, 2)
-  auto pos = [](uint32_t O) -> uint32_t { return (NBLK - 1) - (O & (NBLK - 1)); };
+  auto pos = [](uint32_t O) -> uint32_t { return (NBLK - 1) - (O % NBLK); };
   auto use = [](uint32_t O) -> uint32_t { return (O / NBLK) & 1; };
 
   if (p.dbg & ESRP_DBG_EMPTY) {
@@ -323,9 +332,10 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
         }
         mbar_wait(&blk_empty[pos(On)], use(On));
         tcgen05_fence_after();
-        // accumulator = blocks pos(On), +1, +2; split in two MMAs where it straddles the end of the ring
+        // accumulator = blocks pos(On), +1, +2 (SHADOW: +1 / +2 may be the shadow blocks NBLK / NBLK + 1 of positions 0 / 1);
+        // without shadows it is split in two MMAs where it straddles the end of the ring
         const uint32_t P = pos(On);
-        const uint32_t nA = (P + 3 <= NBLK) ? 3u * BN : (NBLK - P) * BN;  // columns before the wrap
+        const uint32_t nA = (SHADOW || P + 3 <= NBLK) ? 3u * BN : (NBLK - P) * BN;  // columns before the wrap
         const uint32_t nB = 3u * BN - nA;
         const uint32_t dA = tmem_base + P * BN, dB = tmem_base;
         const uint32_t idA = umma_idesc_bf16_m128(nA), idB = umma_idesc_bf16_m128(nB ? nB : 16u);
@@ -486,7 +496,10 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
         const int y = r0 - 1 + j;
         const bool real = y >= sw.ya && y < sw.yb && !(p.dbg & ESRP_DBG_NO_EPI);
         const bool store = real && col_ok;
-        const uint32_t blk = lane_addr + pos(O) * BN;
+        const uint32_t P = pos(O);
+        const uint32_t blk = lane_addr + P * BN;
+        const bool sh = SHADOW && P < 2;                   // part of this row's sum lives in the shadow block of its position
+        const uint32_t blk2 = lane_addr + (NBLK + P) * BN;
         const size_t rowid = static_cast<size_t>(sw.img) * p.h + (real ? y : sw.ya);
         const size_t pix = rowid * p.w + (col_ok ? xs : 0);
         // Element offset of channel c (multiple of 4) of this pixel in an fp32 operand of `ct` channels.  NHWC, or
@@ -513,6 +526,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
 #pragma unroll
           for (int c = 0; c < BN; c += GC) {
             if constexpr (GC == 16) tmem_st_zero_x16(blk + c); else tmem_st_zero_x8(blk + c);
+            if (sh) { if constexpr (GC == 16) tmem_st_zero_x16(blk2 + c); else tmem_st_zero_x8(blk2 + c); }
           }
           tmem_st_wait();
           tcgen05_fence_before();
@@ -530,7 +544,16 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
           uint32_t acc[GC], ax[GC];
           tmem_ld_cols<GC>(blk + ch0, acc);
           if (AUX) tmem_ld_cols<GC>(blk + AUX_COL0 + ch0, ax);
-          tmem_ld_wait();
+          if (sh) {  // (warp-uniform) 2 of every NBLK rows: add the shadow block's part of the sum
+            uint32_t a2[GC];
+            tmem_ld_cols<GC>(blk2 + ch0, a2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < GC; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(a2[i]));
+            if constexpr (GC == 16) tmem_st_zero_x16(blk2 + ch0); else tmem_st_zero_x8(blk2 + ch0);
+          } else {
+            tmem_ld_wait();
+          }
           if constexpr (GC == 16) tmem_st_zero_x16(blk + ch0); else tmem_st_zero_x8(blk + ch0);
           if (g == ROUNDS - 1) {
             tmem_st_wait();

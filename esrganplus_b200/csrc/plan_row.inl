@@ -25,7 +25,7 @@ static int plan_row_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
   const int w_chunk_bytes = 3 * nb_rows * RB;
   const int w_all = d.num_chunks * w_chunk_bytes;
   p.nt = nb_rows;
-  const int nblk = (has_aux || BN == 64) ? 8 : 16;  // TMEM ring of output-row blocks (conv3x3_row.cuh)
+  const int nblk = BN == 64 ? 8 : (has_aux ? 7 : 14);  // ring positions of the TMEM output-row blocks (conv3x3_row.cuh: NBLK)
   if (has_aux && BN == 64) return set_error("conv3x3(row): bn=64 cannot carry the conv1x1 (TMEM)");
   p.mt = nblk;
   p.cw = kRowTile; p.cw_log2 = 7; p.rm = 1;

@@ -214,7 +214,16 @@ def test_conv3x3_coscheduled_slices(cuda_dev, shape, train_ext, issuers):
 
     ob1, of1, pre1 = run(True)
     ob2, of2, pre2 = run(False)
-    assert torch.equal(of1, of2) and torch.equal(ob1, ob2)
+    # A CTA that streams more than ~12 rows has two of every 14 output rows summed as (main block) + (shadow block)
+    # (conv3x3_row.cuh: SHADOW) instead of in one accumulator, and WHICH rows depends on how the rows are cut over the
+    # CTAs — the sliced launch gives every CTA twice the rows.  Same products, another fp32 summation order: equal to
+    # fp32 rounding (and to one bf16 ulp where a value sits on a rounding boundary), bit-identical for short row ranges.
+    def same(a, b, ulp):
+        if n * h * ((w + 127) // 128) <= 12 * 74:
+            return torch.equal(a, b)
+        d = (a.float() - b.float()).abs()
+        return bool((d <= ulp * (a.float().abs() + 1.0)).all())
+    assert same(of1, of2, 2e-6) and same(ob1, ob2, 2 ** -7)
     if not train_ext:
         # fp32 operands in the engine-private [n,h,c/4,w,4] layout (esrp_conv3x3_t::f32_planar): same values
         def to_planar(t):
@@ -231,7 +240,7 @@ def test_conv3x3_coscheduled_slices(cuda_dev, shape, train_ext, issuers):
                    f32_planar=1, variant=issuers).launch()
         assert torch.equal(ob3, ob1) and torch.equal(from_planar(of3), of1)
     if train_ext:
-        assert torch.equal(pre1, pre2)
+        assert same(pre1, pre2, 2e-6)
     # against torch: v = 0.2*conv + r1; noise; 0.2*v + r2  (draws regenerated on the host)
     ref = _ref_conv([t_in, gro], chunks, 64, wt, bias, act=0)
     v = (0.2 * ref + r1.permute(0, 3, 1, 2)).permute(0, 2, 3, 1).contiguous()

@@ -233,6 +233,9 @@ CONFIGS = [  # (TMEM blocks, row buffers, input rows per segment of one CTA)
     # images of a few rows put many segments (each with two extra blocks) behind one another: the planner then keeps two
     # row buffers (plan_row.inl: h <= blocks - 3), otherwise the producer could be lapped on a block barrier
     (8, 2, [3, 1, 2, 1, 12]), (16, 2, [1] * 12), (8, 2, [2] * 9),
+    # ring sizes of the shadow-block layout (conv3x3_row.cuh: NBLK = 14, 7 with the conv1x1; positions are O % NBLK)
+    (14, 2, [16]), (14, 2, [30]), (14, 4, [16]), (14, 12, [30]), (14, 2, [1, 14, 2]), (14, 2, [1] * 12), (14, 6, [15, 3]),
+    (7, 2, [16]), (7, 5, [16]), (7, 5, [9, 7]), (7, 3, [2, 2, 2, 9]), (7, 2, [1]), (7, 2, [2] * 9), (7, 2, [3, 1, 2, 1, 12]),
 ]
 
 
@@ -278,7 +281,7 @@ def test_protocol_on_random_shapes_with_the_planner_rules():
     plan_row.inl bounds it (<= blocks - 2, <= 8, two for images of a few rows): both issuer protocols stay live and safe."""
     rng = random.Random(2024)
     for case in range(250):
-        nblk = rng.choice([8, 16])
+        nblk = rng.choice([7, 8, 14])
         n, h, x_tiles = rng.randrange(1, 600), rng.choice([1, 2, 3, 4, 5, 6, 7, 9, 14, 33, 128]), rng.randrange(1, 3)
         units = n * x_tiles * h
         grid = min(units, rng.choice([148, 74]))
@@ -293,7 +296,9 @@ def test_protocol_on_random_shapes_with_the_planner_rules():
 
 @pytest.mark.parametrize("nblk,stages,chunks,segments", [(16, 2, 3, [28]), (16, 2, 3, [1, 14, 2]), (16, 4, 2, [16]), (8, 4, 2, [15, 3]),
                                                          (16, 2, 2, [2, 2, 2, 9]), (8, 2, 3, [1]), (16, 2, 3, [30, 1, 1]),
-                                                         (16, 3, 2, [40]), (8, 3, 2, [7, 9])])
+                                                         (16, 3, 2, [40]), (8, 3, 2, [7, 9]),
+                                                         (14, 2, 3, [30]), (14, 4, 2, [16]), (14, 2, 3, [1, 14, 2]), (7, 4, 2, [15, 3]),
+                                                         (14, 2, 2, [2, 2, 2, 9]), (7, 2, 3, [1])])
 def test_chunk_barriers_are_live_and_safe(nblk, stages, chunks, segments):
     """ConvKParams::chunk_bars (row-alternating issuers, stages * chunks <= 8): one landed-barrier per K-chunk tile, tiles
     landing in any order; a chunk's MMAs must only ever be issued from a tile that holds that row's chunk, and nobody may be
