@@ -15,6 +15,7 @@ LAYOUT_ROW = 1    # ky-stacked row streaming (conv3x3_row.cuh): images wider tha
 
 
 VARIANT_ROW_ALT = 0x2000   # ESRP_VARIANT_ROW_ALT: row kernel, MMA issuers alternate whole rows (include/esrp.h)
+VARIANT_PAIR = 0x4000      # ESRP_VARIANT_PAIR: row kernel, clusters of two CTAs share every MMA (cta_group::2)
 
 
 def variant_mt(mt: int) -> int:

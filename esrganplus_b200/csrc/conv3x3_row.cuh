@@ -77,11 +77,13 @@ struct SegWalk {
   int img, x0, ya, yb;  // current segment: output rows [ya, yb) of column block x0 of image img
   // cta / ncta: position among the CTAs that split the rows (== blockIdx.x / gridDim.x unless the launch
   // co-schedules output slices, see ConvKParams::nsl)
-  __device__ __forceinline__ SegWalk(const ConvKParams& p, int cta, int ncta) {
+  int img_off;           // CTA pairs: the second CTA walks the same rows of image img + n / 2
+  __device__ __forceinline__ SegWalk(const ConvKParams& p, int cta, int ncta, int img_off_ = 0) {
     const long long U = p.units_total;
     u = static_cast<int>(U * cta / ncta);
     u_end = static_cast<int>(U * (cta + 1) / ncta);
     img = x0 = ya = yb = 0;
+    img_off = img_off_;
   }
   __device__ __forceinline__ bool next(const ConvKParams& p) {
     if (u >= u_end) return false;
@@ -91,6 +93,7 @@ struct SegWalk {
     yb = ya + cnt;
     img = col / p.x_tiles;
     x0 = (col - img * p.x_tiles) * kRowTile;
+    img += img_off;
     u += cnt;
     return true;
   }
@@ -110,11 +113,11 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[GC]) 
 // WRAP = false is the straight-line common case (one N = 3*BN MMA per tap, compile-time descriptors: the
 // issue sequence must stay at ~2 integer ops per MMA because the tensor pipe queues almost nothing);
 // WRAP = true splits every tap in two narrower MMAs where the three blocks straddle the end of the ring.
-template <int KC, int BN, int MW, bool WRAP, int KSN = KC / 16>  // KSN: K-slices of 16 channels to issue (the rest: zero weights)
+template <int KC, int BN, int MW, bool WRAP, int KSN = KC / 16, bool PAIR = false>  // KSN: K-slices of 16 channels to issue (the rest: zero weights)
 __device__ __forceinline__ void issue_taps(uint32_t dA, uint32_t dB, uint32_t idA, uint32_t idB, uint32_t bB,
                                            uint32_t al, uint32_t bl, uint32_t desc_hi, uint32_t w_block_desc) {
   constexpr int RB = KC * 2, KS = KC / 16;
-  constexpr uint32_t ID_FULL = umma_idesc_bf16_m128(3 * BN);
+  constexpr uint32_t ID_FULL = PAIR ? umma_idesc_bf16_m256(3 * BN) : umma_idesc_bf16_m128(3 * BN);
 #pragma unroll
   for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
@@ -123,7 +126,9 @@ __device__ __forceinline__ void issue_taps(uint32_t dA, uint32_t dB, uint32_t id
       if (warp0 != (MW == 0)) continue;
       const uint32_t a_d = al + ((kx * RB + ks * 32) >> 4);  // the 130-pixel row shifted by kx pixels
       const uint32_t b_d = bl + kx * w_block_desc + ((ks * 32) >> 4);
-      if (!WRAP) {
+      if (PAIR) {
+        umma_f16_ss2_2sm(dA, a_d, desc_hi, b_d, desc_hi, ID_FULL, 1u);
+      } else if (!WRAP) {
         umma_f16_ss2(dA, a_d, desc_hi, b_d, desc_hi, ID_FULL, 1u);
       } else {
         umma_f16_ss2(dA, a_d, desc_hi, b_d, desc_hi, idA, 1u);
@@ -133,7 +138,14 @@ __device__ __forceinline__ void issue_taps(uint32_t dA, uint32_t dB, uint32_t id
   }
 }
 
-template <int KC, int BN, bool AUX, bool EXT>
+// PAIR: launched as clusters of two CTAs (cta_group::2).  The two CTAs stream the SAME rows of two different images
+// (img, img + n/2: identical segment structure, so ring positions, barrier phases and TMEM addresses coincide); every MMA is
+// M = 256 x N = 3*BN issued by the leader's issuer warps, each CTA holding HALF of the weight rows (B is split along N), so
+// per MMA a CTA reads 4 KB of A + 1.5 KB of B from shared memory instead of 4 + 3 (the shared-memory port is what bounds
+// the single-CTA steady state) and the resident weights take half the space.  Barriers the issuers wait on live in the
+// leader: the row tiles of both CTAs complete on the leader's full_bar (cta_group::2 TMA), both CTAs' epilogues arrive on the
+// leader's blk_empty; commits are multicast to the blk_full of both CTAs (own producer / epilogue wait locally).
+template <int KC, int BN, bool AUX, bool EXT, bool PAIR = false>
 __global__ void __launch_bounds__(kRowThreads, 1)
 conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                    const __grid_constant__ ConvKParams p) {
@@ -142,20 +154,28 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
   constexpr uint32_t LAYOUT = (KC == 64) ? 2u : 4u;
   constexpr uint32_t SBO = 8 * RB;
   constexpr uint32_t DESC_HI = (SBO >> 4) | (1u << 14) | (LAYOUT << 29);
-  // Ring of output-row blocks.  BN <= 32 (SHADOW): R ring positions plus two SHADOW blocks behind them that stand in for
-  // positions 0 / 1 when the three-block accumulator window of an input row would straddle the end of the ring, so the
-  // window is ALWAYS one contiguous N = 3*BN accumulator (no second, narrower MMA per tap on 2 of every R rows: those cost
-  // 1.5x a plain row).  The rows at positions 0 / 1 then have their sum spread over two blocks (main: the contributions
-  // issued while the window was at the bottom of the ring, shadow: the ones issued from its top); the epilogue adds them.
-  // BN = 64: 8 blocks, power-of-two ring, windows that straddle the end are issued as two MMAs (512 columns leave no
-  // room for shadows without shrinking the ring to 6).
-  constexpr bool SHADOW = BN <= 32;
-  constexpr int NBLK = SHADOW ? (AUX ? 7 : 14) : 8;        // ring positions
+  // Ring of output-row blocks (positions descend with the output sequence number, so that the blocks of the rows r+1, r,
+  // r-1 an input row accumulates into are adjacent).  Default: a power-of-two ring; the accumulator window of 2 of every
+  // NBLK input rows straddles its end and is issued as two narrower MMAs per tap.
+  // SHADOW (the CTA-pair variant, whose B halves must be the same rows for every MMA): NBLK ring positions plus two SHADOW
+  // blocks behind them that stand in for positions 0 / 1 when the window would straddle the end, so the window is ALWAYS
+  // one contiguous N = 3*BN accumulator.  The rows at positions 0 / 1 then have their sum spread over two blocks (main: the
+  // contributions issued while the window was at the bottom of the ring, shadow: the ones issued from its top) and the
+  // epilogue adds them.  Measured on the single-CTA kernel as well (round 2): 1.3 % faster on config 2 (13.04 -> 12.88 ms),
+  // but WHICH rows are summed in two parts depends on how the rows are cut over the CTAs, i.e. a tile's result would
+  // depend on its position in the batch at fp32-rounding level (amplified to bf16 noise by 345 requantising convs): not
+  // worth the invariant, so the default path keeps the split MMAs.
+  constexpr bool SHADOW = PAIR;
+  constexpr int NBLK = SHADOW ? (AUX ? 7 : 14) : ((AUX || BN == 64) ? 8 : 16);  // ring positions
   constexpr int NMAIN = SHADOW ? NBLK + 2 : NBLK;          // main blocks incl. the two shadows
   constexpr int AUX_COL0 = NMAIN * BN;                     // conv1x1 blocks live behind the main blocks
-  constexpr int nb_rows = AUX ? 4 * BN : 3 * BN;
-  constexpr int w_block_bytes = nb_rows * RB;
-  constexpr int w_chunk_bytes = 3 * w_block_bytes;
+  static_assert(!PAIR || (BN == 32 && KC == 64 && !EXT), "CTA pairs: dense-block convs of the inference plan only");
+  constexpr int nb_rows = AUX ? 4 * BN : 3 * BN;           // B rows per tap block in global memory
+  constexpr int w_block_bytes_g = nb_rows * RB;
+  constexpr int w_chunk_bytes_g = 3 * w_block_bytes_g;
+  constexpr int w_block_bytes = (PAIR ? nb_rows / 2 : nb_rows) * RB;  // resident in shared memory (PAIR: this CTA's half:
+  constexpr int w_chunk_bytes = 3 * w_block_bytes;                    //   rows [48 r, 48 r + 48) (+ [96 + 16 r, + 16) conv1x1))
+  constexpr int aux_row0 = PAIR ? 3 * BN / 2 : 3 * BN;     // first conv1x1 row of a resident tap block
   constexpr int GC = BN < 16 ? BN : 16;                    // output channels per epilogue round
   constexpr int ROUNDS = BN / GC;
   static_assert(NBLK <= kMaxBlocks && (NMAIN + (AUX ? NBLK : 0)) * BN <= 512, "TMEM budget");
@@ -192,9 +212,13 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
   // nsl*i .. nsl*i+nsl-1 walk the SAME rows, each with the weights / bias / channel offsets of its own slice.
   // They run in step on neighbouring SMs, so the input rows come from DRAM once and from L2 afterwards, and
   // every CTA owns nsl times more rows (half the halo recomputation of nsl separate launches).
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // 0: leader of the pair
+  const int bid = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int nbid = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int img_off = PAIR ? static_cast<int>(rank) * (p.n >> 1) : 0;
   const int nsl = p.nsl > 1 ? p.nsl : 1;
-  const int sl = nsl > 1 ? static_cast<int>(blockIdx.x) % nsl : 0;
-  const int cta = static_cast<int>(blockIdx.x) / nsl, ncta = static_cast<int>(gridDim.x) / nsl;
+  const int sl = nsl > 1 ? bid % nsl : 0;
+  const int cta = bid / nsl, ncta = nbid / nsl;
   const int csh = sl * BN;                                  // channel shift of every global channel offset
   const uint8_t* const w_src = p.w_packed + static_cast<size_t>(sl) * p.sl_stride;
 
@@ -205,19 +229,24 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     for (int i = 0; i < kMaxBlocks; ++i) {
       // row-alternating issue (row_alt == 2): + one plain arrival of the warp that does NOT issue the completing row
       mbar_init(&blk_full[i], p.row_alt == 2 ? kRowMmaWarps + 1 : kRowMmaWarps);
-      mbar_init(&blk_empty[i], 4);
-      mbar_arrive_cnt(&blk_empty[i], 4);  // phase 0 = "the block is free": complete from the start (no wait relies on the
+      mbar_init(&blk_empty[i], PAIR ? 8 : 4);  // (PAIR: the four warps of a warpgroup of BOTH CTAs; only the leader's is used)
+      mbar_arrive_cnt(&blk_empty[i], PAIR ? 8 : 4);  // phase 0 = "the block is free": complete from the start (no wait relies on the
                                           // parity of a phase that never existed; compute-sanitizer synccheck flags those)
     }
-    mbar_init(wfull, 1);
+    mbar_init(wfull, (PAIR && rank == 0) ? 2 : 1);  // leader of a pair: + the peer's "my half of B has landed"
     mbar_init(&tok[0], 1);
     mbar_init(&tok[1], 1);
     mbar_arrive(&tok[0]);                 // warp 0 holds the first turn
     fence_barrier_init();
   }
   if (warp == kRowEpiWarps + 1) {
-    tmem_alloc(tmem_holder, 512);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_2sm(tmem_holder, 512);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_holder, 512);
+      tmem_relinquish();
+    }
   }
   grid_dep_launch_dependents();
   if (threadIdx.x < BN)  // (weights / bias: written long ago)
@@ -225,7 +254,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
         p.bias ? reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(p.bias) + static_cast<size_t>(sl) * p.sl_stride)[threadIdx.x]
                : 0.f;
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();  // (PAIR: the peer's barriers are initialised too)
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
   // every block starts zeroed: all MMAs accumulate
@@ -235,7 +264,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     tmem_st_wait();
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();  // (PAIR: the peer's blocks are zeroed before the leader issues)
   tcgen05_fence_after();
 
   ESRP_FINE_TRACE(if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[2 * 1024 + 1019] = clock64();)
@@ -253,9 +282,19 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     // row that input completes (one commit per row and warp serves the epilogue and the producer).
     if (lane == 0) {
       mbar_arrive_expect_tx(wfull, static_cast<uint32_t>(w_res_bytes));
-      for (int c = 0; c < p.num_chunks; ++c)
-        bulk_load_1d(w_res + c * w_chunk_bytes, w_src + static_cast<size_t>(c) * w_chunk_bytes,
-                     w_chunk_bytes, wfull);
+      if constexpr (PAIR) {
+        for (int c = 0; c < p.num_chunks; ++c)
+          for (int kx = 0; kx < 3; ++kx) {
+            const uint8_t* src = w_src + static_cast<size_t>(c) * w_chunk_bytes_g + kx * w_block_bytes_g;
+            uint8_t* dst = w_res + c * w_chunk_bytes + kx * w_block_bytes;
+            bulk_load_1d(dst, src + rank * (3 * BN / 2) * RB, (3 * BN / 2) * RB, wfull);
+            if (AUX) bulk_load_1d(dst + aux_row0 * RB, src + (3 * BN + rank * (BN / 2)) * RB, (BN / 2) * RB, wfull);
+          }
+      } else {
+        for (int c = 0; c < p.num_chunks; ++c)
+          bulk_load_1d(w_res + c * w_chunk_bytes, w_src + static_cast<size_t>(c) * w_chunk_bytes,
+                       w_chunk_bytes, wfull);
+      }
       uint32_t tn = 0;
       trace_ev(p, 0, tn);
       grid_dep_wait();  // activations of the previous kernel must be complete before the first TMA load
@@ -264,7 +303,8 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
       int b = 0;
       uint32_t I = 0, O0 = 0;
       uint8_t* st = stage0;
-      SegWalk sw(p, cta, ncta);
+      SegWalk sw(p, cta, ncta, img_off);
+      const uint32_t full0 = PAIR ? mapa_u32(smem_u32(full_bar), 0) : smem_u32(full_bar);  // (PAIR: the LEADER's barriers)
       while (sw.next(p)) {
         const int r0 = max(sw.ya - 1, 0), r1 = min(sw.yb, p.h - 1);
         for (int r = r0; r <= r1; ++r, ++I) {
@@ -279,7 +319,21 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
             if (++b == D) { b = 0; st = stage0; }
             continue;
           }
-          if (p.chunk_bars) {  // one barrier per chunk tile: full_bar[b * nch + c]
+          if constexpr (PAIR) {
+            // both CTAs' tiles are counted on the leader's barrier (which expects twice the bytes); the peer only loads
+            if (p.chunk_bars) {
+              for (int c = 0; c < nch; ++c) {
+                if (rank == 0) mbar_arrive_expect_tx(&full_bar[b * nch + c], 2u * static_cast<uint32_t>(p.a_box_bytes));
+                tma_load_4d_hint_2sm(st + c * a_bytes, p.chunk_src[c] ? &tm1 : &tm0, full0 + 8u * (b * nch + c), p.chunk_c0[c],
+                                     sw.x0 - 1, r, sw.img, kL2EvictLast);
+              }
+            } else {
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[b], 2u * tx_bytes);
+              for (int c = 0; c < nch; ++c)
+                tma_load_4d_hint_2sm(st + c * a_bytes, p.chunk_src[c] ? &tm1 : &tm0, full0 + 8u * b, p.chunk_c0[c], sw.x0 - 1, r,
+                                     sw.img, kL2EvictLast);
+            }
+          } else if (p.chunk_bars) {  // one barrier per chunk tile: full_bar[b * nch + c]
             for (int c = 0; c < nch; ++c) {
               mbar_arrive_expect_tx(&full_bar[b * nch + c], static_cast<uint32_t>(p.a_box_bytes));
               tma_load_4d_hint(st + c * a_bytes, p.chunk_src[c] ? &tm1 : &tm0, &full_bar[b * nch + c], p.chunk_c0[c], sw.x0 - 1, r,
@@ -298,6 +352,12 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
       }
       trace_ev(p, 0, tn);
     }
+  } else if (PAIR && rank != 0 && warp > kRowEpiWarps) {
+    // peer CTA of a pair: nothing to issue; one warp tells the leader when this CTA's half of B has landed
+    if (warp == kRowEpiWarps + 1) {
+      mbar_wait(wfull, 0);
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(wfull), 0));
+    }
   } else if (warp > kRowEpiWarps) {
     // ====================================== MMA issuers ======================================
     const int mw = warp - (kRowEpiWarps + 1);
@@ -308,7 +368,13 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     const uint32_t row_step = static_cast<uint32_t>(row_bytes) >> 4, chunk_step = static_cast<uint32_t>(a_bytes) >> 4;
     constexpr uint32_t w_step = static_cast<uint32_t>(w_chunk_bytes) >> 4;
     constexpr uint32_t w_block_desc = static_cast<uint32_t>(w_block_bytes) >> 4;
-    const uint32_t idesc_aux = umma_idesc_bf16_m128(BN);
+    const uint32_t idesc_aux = PAIR ? umma_idesc_bf16_m256(BN) : umma_idesc_bf16_m128(BN);
+    // commit / plain arrival on a block barrier (PAIR: of both CTAs)
+    auto commit = [](uint64_t* bar) { if constexpr (PAIR) umma_commit_2sm(bar); else umma_commit(bar); };
+    auto arrive_blk = [](uint64_t* bar) {
+      mbar_arrive(bar);
+      if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(bar), 1));
+    };
     uint32_t tn = 0;
     if (mw == 0 && lane == 0) trace_ev(p, 1, tn);
     int b = 0;
@@ -359,8 +425,8 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
               for (int c = 0; c < nfull; ++c, al += chunk_step, bl += w_step) {
                 if (p.chunk_bars && c > 0) { mbar_wait(&full_bar[b * nch + c], fph); tcgen05_fence_after(); }
                 if (nB == 0) {
-                  issue_taps<KC, BN, 0, false>(dA, dB, idA, idB, bB, al, bl, DESC_HI, w_block_desc);
-                  issue_taps<KC, BN, 1, false>(dA, dB, idA, idB, bB, al, bl, DESC_HI, w_block_desc);
+                  issue_taps<KC, BN, 0, false, KS, PAIR>(dA, dB, idA, idB, bB, al, bl, DESC_HI, w_block_desc);
+                  issue_taps<KC, BN, 1, false, KS, PAIR>(dA, dB, idA, idB, bB, al, bl, DESC_HI, w_block_desc);
                 } else {
                   issue_taps<KC, BN, 0, true>(dA, dB, idA, idB, bB, al, bl, DESC_HI, w_block_desc);
                   issue_taps<KC, BN, 1, true>(dA, dB, idA, idB, bB, al, bl, DESC_HI, w_block_desc);
@@ -369,8 +435,8 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
               if (p.chunk_bars && nfull < nch && nfull > 0) { mbar_wait(&full_bar[b * nch + nfull], fph); tcgen05_fence_after(); }
               if (nfull < nch) {  // last chunk: only its first half carries weights (K = 96 / 160 in 64-channel chunks)
                 if (nB == 0) {
-                  issue_taps<KC, BN, 0, false, KS / 2>(dA, dB, idA, idB, bB, al, bl, DESC_HI, w_block_desc);
-                  issue_taps<KC, BN, 1, false, KS / 2>(dA, dB, idA, idB, bB, al, bl, DESC_HI, w_block_desc);
+                  issue_taps<KC, BN, 0, false, KS / 2, PAIR>(dA, dB, idA, idB, bB, al, bl, DESC_HI, w_block_desc);
+                  issue_taps<KC, BN, 1, false, KS / 2, PAIR>(dA, dB, idA, idB, bB, al, bl, DESC_HI, w_block_desc);
                 } else {
                   issue_taps<KC, BN, 0, true, KS / 2>(dA, dB, idA, idB, bB, al, bl, DESC_HI, w_block_desc);
                   issue_taps<KC, BN, 1, true, KS / 2>(dA, dB, idA, idB, bB, al, bl, DESC_HI, w_block_desc);
@@ -382,20 +448,25 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
                 for (int c = 0; c < naux; ++c, al += chunk_step, bl += w_step) {
 #pragma unroll
                   for (int ks = 0; ks < KS; ++ks)
+                    if constexpr (PAIR)
+                      umma_f16_ss2_2sm(d_aux, al + ((1 * RB + ks * 32) >> 4), DESC_HI,
+                                       bl + w_block_desc + ((aux_row0 * RB + ks * 32) >> 4), DESC_HI, idesc_aux,
+                                       (c | ks) != 0 ? 1u : 0u);
+                    else
                     umma_f16_ss2(d_aux, al + ((1 * RB + ks * 32) >> 4), DESC_HI,
-                                 bl + w_block_desc + ((3 * BN * RB + ks * 32) >> 4), DESC_HI, idesc_aux,
+                                 bl + w_block_desc + ((aux_row0 * RB + ks * 32) >> 4), DESC_HI, idesc_aux,
                                  (c | ks) != 0 ? 1u : 0u);
                 }
               }
               ESRP_FINE_TRACE(if (mw == 0) trace_ev(p, 1, tn);)  // MMAs issued
               mbar_arrive(&tok[mw ^ 1]);                // the other warp's turn
-              umma_commit(&blk_full[pos(O0 + k)]);      // final contributor of output row r-1
-              umma_commit(&blk_full[pos(O0 + k + 1)]);  // middle contributor of output row r
-              if (k == 0) umma_commit(&blk_full[pos(O0)]);  // (dummy) first block: no earlier row
+              commit(&blk_full[pos(O0 + k)]);      // final contributor of output row r-1
+              commit(&blk_full[pos(O0 + k + 1)]);  // middle contributor of output row r
+              if (k == 0) commit(&blk_full[pos(O0)]);  // (dummy) first block: no earlier row
               if (k == ni - 1) {                        // last input row of the segment: no later row
-                umma_commit(&blk_full[pos(O0 + k + 1)]);
-                umma_commit(&blk_full[pos(O0 + k + 2)]);
-                umma_commit(&blk_full[pos(O0 + k + 2)]);
+                commit(&blk_full[pos(O0 + k + 1)]);
+                commit(&blk_full[pos(O0 + k + 2)]);
+                commit(&blk_full[pos(O0 + k + 2)]);
               }
             }
             __syncwarp();
@@ -409,10 +480,10 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
             // k-1, issued by THIS warp, and row k.  No later row of this warp commits on its block, so the arrival is a
             // commit here: it tracks this thread's MMAs of row k-1 (found by tests/test_row_protocol_model.py).
             if (elect_one()) {
-              mbar_arrive(&blk_full[pos(O0 + k)]);
+              arrive_blk(&blk_full[pos(O0 + k)]);
               if (k == ni - 1) {
-                umma_commit(&blk_full[pos(O0 + k + 1)]);
-                mbar_arrive(&blk_full[pos(O0 + k + 2)]);
+                commit(&blk_full[pos(O0 + k + 1)]);
+                arrive_blk(&blk_full[pos(O0 + k + 2)]);
               }
             }
             __syncwarp();
@@ -449,15 +520,15 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
 #pragma unroll
               for (int ks = 0; ks < KS; ++ks)
                 umma_f16_ss2(d_aux, al + ((1 * RB + ks * 32) >> 4), DESC_HI,
-                             bl + w_block_desc + ((3 * BN * RB + ks * 32) >> 4), DESC_HI, idesc_aux,
+                             bl + w_block_desc + ((aux_row0 * RB + ks * 32) >> 4), DESC_HI, idesc_aux,
                              (c | ks) != 0 ? 1u : 0u);
             }
           }
           mbar_arrive(&tok[mw ^ 1]);             // the other warp's turn
-          umma_commit(&blk_full[pos(O0 + k)]);  // output row r-1 has all its contributions (from this warp)
+          commit(&blk_full[pos(O0 + k)]);  // output row r-1 has all its contributions (from this warp)
           if (k == ni - 1) {                    // last input row of the segment completes the other two as well
-            umma_commit(&blk_full[pos(O0 + k + 1)]);
-            umma_commit(&blk_full[pos(O0 + k + 2)]);
+            commit(&blk_full[pos(O0 + k + 1)]);
+            commit(&blk_full[pos(O0 + k + 2)]);
           }
         }
         __syncwarp();
@@ -481,7 +552,12 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     int turn = 0;
     if (threadIdx.x == 0) trace_ev(p, 2, tn);
     grid_dep_wait();  // residual reads / output writes must not race with the previous kernel
-    SegWalk sw(p, cta, ncta);
+    SegWalk sw(p, cta, ncta, img_off);
+    // "block read + zeroed": the issuers (of the leader) wait for it
+    const uint32_t empty0 = (PAIR && rank != 0) ? mapa_u32(smem_u32(blk_empty), 0) : 0u;
+    auto release_blk = [&](uint32_t P_) {
+      if (PAIR && rank != 0) mbar_arrive_cluster(empty0 + 8u * P_); else mbar_arrive(&blk_empty[P_]);
+    };
     while (sw.next(p)) {
       const int r0 = max(sw.ya - 1, 0), r1 = min(sw.yb, p.h - 1);
       const int xs = sw.x0 + xl;
@@ -531,7 +607,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
           tmem_st_wait();
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&blk_empty[pos(O)]);
+          if (lane == 0) release_blk(P);
           continue;
         }
         uint32_t pend[8];  // bf16 output of an even round, stored together with the following odd round
@@ -559,7 +635,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
             tmem_st_wait();
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&blk_empty[pos(O)]);
+            if (lane == 0) release_blk(P);
             ESRP_FINE_TRACE(if (threadIdx.x == 0) trace_ev(p, 2, tn);)  // block released
           }
           if (ch0 >= p.cout) continue;  // (warp-uniform; lanes of columns >= w compute along and store nothing)
@@ -697,10 +773,10 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();  // (PAIR: no CTA leaves while its peer may still reach into it)
   if (warp == kRowEpiWarps + 1) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (PAIR) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
   ESRP_FINE_TRACE(if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) { p.trace[2 * 1024 + 1021] = clock64(); long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); p.trace[2 * 1024 + 1020] = gt; })
   ESRP_FINE_TRACE(if (p.trace && threadIdx.x == 0 && blockIdx.x < 512) { long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); p.trace[1024 + 512 + blockIdx.x] = gt; })

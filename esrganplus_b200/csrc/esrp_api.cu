@@ -123,12 +123,23 @@ int run_conv(const ConvLaunch& L, cudaStream_t stream) {
   cfg.blockDim = dim3(L.threads);
   cfg.dynamicSmemBytes = L.smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
   static const bool no_pdl = getenv("ESRP_NO_PDL") != nullptr;
+  if (!no_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (L.cluster > 1) {  // CTA pairs of the row kernel (cta_group::2)
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = L.cluster;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = no_pdl ? 0 : 1;
+  cfg.numAttrs = na;
   ESRP_CUDA_OK(cudaLaunchKernelExC(&cfg, L.kernel, args));
   return 0;
 }

@@ -20,7 +20,7 @@ static_assert(kChainMaxPhasesHost == kChainMaxPhases, "keep esrp_host.h in step 
 
 bool chain_compatible(const ConvLaunch& L) {
   const ConvKParams& p = L.params;
-  return L.fam == 1 && L.kc == 64 && L.bn == 32 && L.ext == 0 && p.out_nchw == nullptr && p.trace == nullptr && p.dbg == 0 &&
+  return L.fam == 1 && L.cluster == 1 && L.kc == 64 && L.bn == 32 && L.ext == 0 && p.out_nchw == nullptr && p.trace == nullptr && p.dbg == 0 &&
          p.w_resident == 1 && L.grid >= 1 && p.cout == 32 && p.act != 2 && p.num_chunks <= 4 && p.noise == 0 && p.seed_ptr == nullptr &&
          (p.r1 == nullptr || p.s1 == 1.0f) && p.bias != nullptr && (p.nsl <= 1 || p.sl_stride % 16 == 0);
 }

@@ -30,6 +30,7 @@ struct ConvLaunch {
   // which kernel family / instantiation `kernel` is (the chain builder merges compatible row-kernel launches)
   int fam = 0;  // 0: tile kernel (conv3x3_tc.cuh), 1: row kernel (conv3x3_row.cuh)
   int kc = 0, bn = 0, ext = 0;
+  int cluster = 1;  // CTAs per thread-block cluster (2: the row kernel's cta_group::2 pairs)
 };
 int plan_conv(const esrp_conv3x3_t& d, ConvLaunch* out);
 // per-family planners (esrp_conv_{row,tile}{,_ext}.cu); *_ext carry the training extensions of the fused tail

@@ -268,6 +268,79 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t count) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// CTA pairs (thread-block cluster of 2, tcgen05 cta_group::2): one MMA spans the tensor cores of both SMs (M = 256: each
+// CTA supplies its own 128 rows of A and HALF of the B rows, the accumulator lanes of each CTA's rows live in its own
+// tensor memory at the same columns), issued by a thread of the leader CTA (rank 0).
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+// All threads of all CTAs of the cluster.
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+// arrive on a barrier of another CTA of the cluster (address from mapa_u32)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+// 4-D tiled load into THIS CTA's shared memory whose completion bytes are counted on a barrier that may live in the peer
+// CTA of the pair (bar_cluster_addr: from mapa_u32): the leader's barrier collects the tiles of both CTAs.
+__device__ __forceinline__ void tma_load_4d_hint_2sm(void* smem_dst, const void* tmap, uint32_t bar_cluster_addr, int c0, int c1,
+                                                     int c2, int c3, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;\n"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr),
+        "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+      : "memory");
+}
+// Whole warp, the same warp index in BOTH CTAs of the pair, the same holder offset.
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_holder, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_holder)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[128 rows from each CTA's shared memory] * B[N/2 rows from each CTA's shared memory]; the
+// descriptors are shared-memory OFFSETS that both CTAs apply to their own window.
+__device__ __forceinline__ void umma_f16_ss2_2sm(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on the barrier at this shared-memory offset in BOTH CTAs of the pair when all previously issued tcgen05.mma of
+// this thread have completed.
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
 // UMMA descriptors (bit layouts: PTX ISA "tcgen05 matrix / instruction descriptor")
 // ----------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, K-major operand with 32/64/128-byte swizzle.
@@ -288,6 +361,10 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t sbo_
 // Instruction descriptor for kind::f16, BF16 x BF16 -> F32, both operands K-major, M = 128.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_m128(uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+// The same with M = 256 (cta_group::2: 128 rows per CTA of the pair).
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_m256(uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((256u >> 4) << 24);
 }
 
 }  // namespace esrp

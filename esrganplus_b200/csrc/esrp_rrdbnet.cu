@@ -356,6 +356,11 @@ int build_plan(Rrdbnet* m, int n, int h, int w, uint8_t* wsp, int training, cuda
     st.kind = Step::kConv;
     esrp_conv3x3_t d = d0;
     d.variant |= ESRP_VARIANT_ROW_ALT;  // inference plans: row-alternating MMA issuers where the row kernel runs
+    // CTA pairs for the dense-block convs of an even batch: opt-in (ESRP_PAIR=1), measured SLOWER on config 2 (14.45 vs
+    // 13.10 ms); not when the convs are to be merged into a chain
+    static const bool env_chain = [] { const char* e = getenv("ESRP_CHAIN"); return e && atoi(e) != 0; }();
+    static const bool env_pair = [] { const char* e = getenv("ESRP_PAIR"); return e && atoi(e) != 0; }();
+    if (env_pair && !m->use_chain && !env_chain) d.variant |= ESRP_VARIANT_PAIR;
     if (plan_conv(d, &st.conv)) return 1;
     st.patch_y = patch_y;
     st.is_noise = is_noise;

@@ -14,7 +14,8 @@
 namespace esrp {
 
 // ky-stacked row-streaming kernel (conv3x3_row.cuh)
-template <int KC, int BN, bool AUX, bool EXT>
+// PAIR: clusters of two CTAs (cta_group::2 MMAs over two images, half of the weight rows resident per CTA; conv3x3_row.cuh)
+template <int KC, int BN, bool AUX, bool EXT, bool PAIR = false>
 static int plan_row_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
   constexpr int RB = KC * 2;
   ConvKParams& p = out->params;
@@ -22,17 +23,17 @@ static int plan_row_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
   p.n = d.n; p.h = d.h; p.w = d.w;
   const bool has_aux = d.aux_chunks > 0;
   const int nb_rows = (has_aux ? 4 : 3) * BN;
-  const int w_chunk_bytes = 3 * nb_rows * RB;
+  const int w_chunk_bytes = 3 * (PAIR ? nb_rows / 2 : nb_rows) * RB;  // resident per CTA
   const int w_all = d.num_chunks * w_chunk_bytes;
   p.nt = nb_rows;
-  const int nblk = BN == 64 ? 8 : (has_aux ? 7 : 14);  // ring positions of the TMEM output-row blocks (conv3x3_row.cuh: NBLK)
+  const int nblk = PAIR ? (has_aux ? 7 : 14) : ((has_aux || BN == 64) ? 8 : 16);  // ring positions of the TMEM output-row blocks (conv3x3_row.cuh: NBLK)
   if (has_aux && BN == 64) return set_error("conv3x3(row): bn=64 cannot carry the conv1x1 (TMEM)");
   p.mt = nblk;
   p.cw = kRowTile; p.cw_log2 = 7; p.rm = 1;
   p.x_tiles = (d.w + kRowTile - 1) / kRowTile;
   p.x_step = kRowTile;
   p.units_per_col = d.h;
-  p.units_total = static_cast<long long>(d.n) * p.x_tiles * d.h;
+  p.units_total = static_cast<long long>(PAIR ? d.n / 2 : d.n) * p.x_tiles * d.h;  // (PAIR: rows of the first half of the batch)
   if (p.units_total > 0x7fffffffLL) return set_error("conv3x3: problem too large (%lld rows)", p.units_total);
   p.a_box_bytes = (kRowTile + 2) * RB;
   p.a_stage_bytes = (p.a_box_bytes + 1023) / 1024 * 1024;
@@ -75,7 +76,7 @@ static int plan_row_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
   } else {
     out->tm1 = out->tm0;
   }
-  auto kern = conv3x3_row_kernel<KC, BN, AUX, EXT>;
+  auto kern = conv3x3_row_kernel<KC, BN, AUX, EXT, PAIR>;
   if (ensure_max_smem(reinterpret_cast<const void*>(kern))) return 1;
   out->kernel = reinterpret_cast<const void*>(kern);
   out->threads = kRowThreads;
@@ -83,8 +84,10 @@ static int plan_row_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
   const int sms = sm_count();
   if (sms <= 0) return set_error("conv3x3: no CUDA device");
   // co-scheduled slices: groups of nsl CTAs share a row range
-  const int groups = sms / p.nsl < 1 ? 1 : sms / p.nsl;
-  out->grid = (p.units_total < groups ? static_cast<int>(p.units_total) : groups) * p.nsl;
+  const int per = p.nsl * (PAIR ? 2 : 1);  // CTAs that share a row range
+  const int groups = sms / per < 1 ? 1 : sms / per;
+  out->grid = (p.units_total < groups ? static_cast<int>(p.units_total) : groups) * per;
+  out->cluster = PAIR ? 2 : 1;
   return 0;
 }
 
@@ -95,6 +98,17 @@ int ESRP_PLAN_ROW_NAME(const esrp_conv3x3_t& d, ConvLaunch* out) {
   if constexpr (!X) {
     if (d.kc == 64 && d.bn == 16) return aux ? plan_row_t<64, 16, true, false>(d, out) : plan_row_t<64, 16, false, false>(d, out);
     if (d.kc == 32 && d.bn == 16) return aux ? plan_row_t<32, 16, true, false>(d, out) : plan_row_t<32, 16, false, false>(d, out);
+  }
+  if constexpr (!X) {
+    // CTA pairs (ESRP_VARIANT_PAIR, with the row-alternating issuers, on an even batch).  ESRP_PAIR=0 switches them off.
+    static const int pair_env = [] { const char* e = getenv("ESRP_PAIR"); return e ? atoi(e) : 1; }();
+    static const int row_alt_env = [] { const char* e = getenv("ESRP_ROW_ALT"); return e ? atoi(e) : -1; }();
+    const bool row_alt = row_alt_env >= 0 ? row_alt_env != 0 : (d.variant & ESRP_VARIANT_ROW_ALT) != 0;
+    // (experiments: ESRP_PAIR_CHUNKS = bit mask of the K-chunk counts that may run as pairs, e.g. 8 = the three-chunk convs)
+    static const int pair_chunks = [] { const char* e = getenv("ESRP_PAIR_CHUNKS"); return e ? atoi(e) : ~0; }();
+    if (pair_env && ((pair_chunks >> d.num_chunks) & 1) && (d.variant & ESRP_VARIANT_PAIR) && row_alt && d.kc == 64 && d.bn == 32 && d.n >= 2 && (d.n % 2) == 0 && (d.variant & 0x1F00) == 0 &&
+        sm_count() >= 2)
+      return aux ? plan_row_t<64, 32, true, false, true>(d, out) : plan_row_t<64, 32, false, false, true>(d, out);
   }
   if (d.kc == 64 && d.bn == 32) return aux ? plan_row_t<64, 32, true, X>(d, out) : plan_row_t<64, 32, false, X>(d, out);
   if (d.kc == 32 && d.bn == 32) return aux ? plan_row_t<32, 32, true, X>(d, out) : plan_row_t<32, 32, false, X>(d, out);

@@ -37,6 +37,11 @@ extern "C" {
  * launch: the engine sets it for its inference plans, where it has been stress-tested.
  * The environment variable ESRP_ROW_ALT=0 / 2 overrides every launch (off / on). */
 #define ESRP_VARIANT_ROW_ALT 0x2000
+/* Row kernel, together with ESRP_VARIANT_ROW_ALT, kc = 64, bn = 32, an even batch: launch clusters of two CTAs that
+ * stream the same rows of images i and i + n/2 and share every MMA (tcgen05 cta_group::2, M = 256; each CTA keeps half
+ * of the weight rows resident).  Experimental: measured slower than the single-CTA launches on the benchmark forward
+ * (DESIGN.md section 4.9), so the engine only sets it when ESRP_PAIR=1; ESRP_PAIR=0 switches it off everywhere. */
+#define ESRP_VARIANT_PAIR 0x4000
 /* Timing experiments (row kernel; the conv result is WRONG with any of these set). */
 #define ESRP_DBG_NO_XHALO 0x100 /* load boxes at x0 instead of x0-1 (no out-of-bounds on the left)  */
 #define ESRP_DBG_NO_MMA 0x200   /* TMA only: stages are released without issuing MMAs              */
