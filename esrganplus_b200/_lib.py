@@ -169,6 +169,7 @@ SYMBOLS = {
     "esrp_rrdbnet_num_launches": (C.c_int32, [C.c_void_p]),
     "esrp_rrdbnet_set_chain": (C.c_int, [C.c_void_p, C.c_int32]),
     "esrp_rrdbnet_num_chained_convs": (C.c_int32, [C.c_void_p]),
+    "esrp_rrdbnet_num_pair_launches": (C.c_int32, [C.c_void_p]),
     "esrp_rrdbnet_set_timing": (C.c_int, [C.c_void_p, C.c_int32]),
     "esrp_rrdbnet_get_timing": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float), C.c_int32]),
     "esrp_rrdbnet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,

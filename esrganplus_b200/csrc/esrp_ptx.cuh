@@ -277,8 +277,10 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
   return r;
 }
-// All threads of all CTAs of the cluster.
+// All threads of all CTAs of the cluster.  The .aligned forms need the whole warp at the same instruction: a warp whose
+// lanes took different role branches (one elected lane looping, 31 lanes falling through) must reconverge first.
 __device__ __forceinline__ void cluster_sync_all() {
+  __syncwarp();
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
 // shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster

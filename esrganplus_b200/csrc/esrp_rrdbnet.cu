@@ -544,6 +544,15 @@ int32_t esrp_rrdbnet_num_chained_convs(const esrp_rrdbnet_t* h) {
   return n;
 }
 
+int32_t esrp_rrdbnet_num_pair_launches(const esrp_rrdbnet_t* h) {
+  const Rrdbnet* m = reinterpret_cast<const Rrdbnet*>(h);
+  if (!m) return -1;
+  int32_t n = 0;
+  for (const Step& st : m->steps)
+    if (st.kind == Step::kConv && st.conv.cluster == 2) ++n;
+  return n;
+}
+
 int esrp_rrdbnet_forward(esrp_rrdbnet_t* h, const float* x, float* y, int32_t n, int32_t hh, int32_t w,
                          void* workspace, int64_t workspace_bytes, int32_t training, uint64_t seed, void* stream) {
   Rrdbnet* m = reinterpret_cast<Rrdbnet*>(h);

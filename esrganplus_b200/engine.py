@@ -140,6 +140,11 @@ class GeneratorEngine:
         """Conv launches that the persistent chains of the last planned forward replaced."""
         return self.lib.esrp_rrdbnet_num_chained_convs(self.handle)
 
+    @property
+    def num_pair_launches(self) -> int:
+        """Conv launches of the last planned forward that run as CTA pairs (cta_group::2; ESRP_PAIR=1 only)."""
+        return self.lib.esrp_rrdbnet_num_pair_launches(self.handle)
+
     def set_timing(self, enable: bool) -> None:
         """Bracket the dense-block convs of the trunk of every following forward with CUDA events (esrp_rrdbnet_set_timing)."""
         _lib.check(self.lib.esrp_rrdbnet_set_timing(self.handle, int(bool(enable))), "esrp_rrdbnet_set_timing")

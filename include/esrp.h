@@ -427,6 +427,8 @@ int esrp_rrdbnet_set_timing(esrp_rrdbnet_t* h, int32_t enable);
 int32_t esrp_rrdbnet_get_timing(esrp_rrdbnet_t* h, float* ms, int32_t max);
 /* Conv launches the chains of the most recently planned forward replaced (0 when none was built). */
 int32_t esrp_rrdbnet_num_chained_convs(const esrp_rrdbnet_t* h);
+/* Conv launches of the most recently planned forward that run as clusters of two CTAs (ESRP_VARIANT_PAIR; 0 unless ESRP_PAIR=1). */
+int32_t esrp_rrdbnet_num_pair_launches(const esrp_rrdbnet_t* h);
 /* x: NCHW fp32 [n,in_nc,h,w] -> y: NCHW fp32 [n,out_nc,upscale*h,upscale*w] (unclamped, like the
  * reference).  training!=0 enables the per-RDB multiplicative Gaussian noise (block.py:117-121)
  * drawn from Philox(seed).  workspace: 1024-byte aligned device memory of at least

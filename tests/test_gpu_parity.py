@@ -766,7 +766,7 @@ net = E.RRDBNet(3, 3, 64, 2); net.load_state_dict(random_state_dict_g(3, 3, 64, 
 x = torch.rand(4, 3, 40, 136, generator=torch.Generator().manual_seed(3)).cuda()
 with torch.no_grad():
     y = net(x)
-torch.save(y.cpu(), sys.argv[2])
+torch.save({"y": y.cpu(), "pairs": net._engines[x.device].num_pair_launches}, sys.argv[2])
 """
 
 
@@ -784,6 +784,6 @@ def test_engine_with_cta_pairs_matches_default_engine(cuda_dev, tmp_path):
         r = subprocess.run([sys.executable, "-c", _PAIR_SCRIPT, root, str(f)], env=env, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(torch.load(f))
-    assert torch.isfinite(outs[1]).all()
-    _net_close(outs[1], outs[0], "ESRP_PAIR=1 vs default")
-    assert not torch.equal(outs[0], outs[1]), "the pair kernels did not run (identical bits)"
+    assert outs[0]["pairs"] == 0 and outs[1]["pairs"] == 2 * 3 * 5, (outs[0]["pairs"], outs[1]["pairs"])   # every dense-block conv
+    # (a CTA streams only a few rows here, no output row is summed over two blocks: the results are normally identical)
+    _net_close(outs[1]["y"], outs[0]["y"], "ESRP_PAIR=1 vs default")
