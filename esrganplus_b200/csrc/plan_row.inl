@@ -101,12 +101,15 @@ int ESRP_PLAN_ROW_NAME(const esrp_conv3x3_t& d, ConvLaunch* out) {
   }
   if constexpr (!X) {
     // CTA pairs (ESRP_VARIANT_PAIR, with the row-alternating issuers, on an even batch).  ESRP_PAIR=0 switches them off.
+    // Not for co-scheduled slices (conv5): that combination passed its parity cases and memcheck but faulted (illegal
+    // address at a multicast commit) under two timing perturbations - a single-issuer experiment and compute-sanitizer
+    // racecheck - and the cause was not found; such launches stay on single CTAs.
     static const int pair_env = [] { const char* e = getenv("ESRP_PAIR"); return e ? atoi(e) : 1; }();
     static const int row_alt_env = [] { const char* e = getenv("ESRP_ROW_ALT"); return e ? atoi(e) : -1; }();
     const bool row_alt = row_alt_env >= 0 ? row_alt_env != 0 : (d.variant & ESRP_VARIANT_ROW_ALT) != 0;
     // (experiments: ESRP_PAIR_CHUNKS = bit mask of the K-chunk counts that may run as pairs, e.g. 8 = the three-chunk convs)
     static const int pair_chunks = [] { const char* e = getenv("ESRP_PAIR_CHUNKS"); return e ? atoi(e) : ~0; }();
-    if (pair_env && ((pair_chunks >> d.num_chunks) & 1) && (d.variant & ESRP_VARIANT_PAIR) && row_alt && d.kc == 64 && d.bn == 32 && d.n >= 2 && (d.n % 2) == 0 && (d.variant & 0x1F00) == 0 &&
+    if (pair_env && ((pair_chunks >> d.num_chunks) & 1) && (d.variant & ESRP_VARIANT_PAIR) && d.slices <= 1 && row_alt && d.kc == 64 && d.bn == 32 && d.n >= 2 && (d.n % 2) == 0 && (d.variant & 0x1F00) == 0 &&
         sm_count() >= 2)
       return aux ? plan_row_t<64, 32, true, false, true>(d, out) : plan_row_t<64, 32, false, false, true>(d, out);
   }
