@@ -309,3 +309,185 @@ def test_chunk_barriers_are_live_and_safe(nblk, stages, chunks, segments):
         m, dead = run(2, nblk, stages, segments, seed, chunks=chunks)
         assert dead is None, (nblk, stages, chunks, segments, seed, dead)
         assert not m.errors, (seed, m.errors[:3])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CTA pairs (conv3x3_row_kernel<..., PAIR = true>, tcgen05 cta_group::2): the same protocol over two CTAs.
+# ---------------------------------------------------------------------------------------------------------------------
+class PairModel(Model):
+    """Leader (CTA 0) and peer (CTA 1) stream the same row sequence.  The issuers live in the leader only and run the
+    row-alternating protocol (mode 2).  Barriers the issuers wait on live in the leader: `full` collects the leader
+    producer's arrival (expect_tx of both tiles) plus the landing of BOTH CTAs' tiles; `blk_empty` one arrival per CTA (a
+    warpgroup of each).  Every commit is multicast: it arrives on `blk_full` of both CTAs, as does the idle warp's plain
+    arrival; each CTA's producer and epilogues wait on their own copy.  Besides liveness / safety in both CTAs the model
+    checks that NOTHING asynchronous is in flight when the last agent finishes — the moment both CTAs pass the final cluster
+    barrier and leave (a multicast arrival after that would hit a CTA that is gone)."""
+
+    def __init__(self, nblk, stages, segments, rng):
+        super().__init__(2, nblk, stages, segments, rng, 1)
+        self.full = [Bar(3) for _ in range(stages)]                 # leader producer + tile of CTA 0 + tile of CTA 1
+        self.blk_full2 = [self.blk_full, [Bar(3) for _ in range(nblk)]]
+        self.blk_empty = [Bar(2) for _ in range(nblk)]
+        self.buf_row2 = [[None] * stages, [None] * stages]
+        self.tile_row2 = [[None] * stages, [None] * stages]
+        self.blk_owner2 = [[None] * nblk, [None] * nblk]
+
+    def producer2(self, cta):
+        buf_bar, buf_par = [0] * self.D, [0] * self.D
+        I, O0, b = 0, 0, 0
+        for ni in self.segs:
+            for k in range(ni):
+                if I >= self.D:
+                    bb, pp = self.blk_full2[cta][buf_bar[b]], buf_par[b]
+                    yield lambda bb=bb, pp=pp: bb.passed(pp)
+                    old = self.buf_row2[cta][b]
+                    ts = self.issued_by.get(old, ())
+                    if not ts or any((t, old) not in self.mma_done for t in ts):
+                        self.errors.append(f"CTA {cta}: buffer {b} refilled while row {old} is not complete")
+                oc = O0 + k
+                buf_bar[b], buf_par[b] = self.pos(oc), self.use(oc)
+                self.buf_row2[cta][b] = I
+                if cta == 0:
+                    self.full[b].arrive()                            # arrive.expect_tx(bytes of both tiles)
+                self.tma.append((cta, b, I))
+                yield None
+                I, b = I + 1, (b + 1) % self.D
+            O0 += ni + 2
+
+    def issuer(self, mw):
+        b, fph, tph, O0, I = 0, 0, 0, 0, 0
+        both = lambda bars, o: [bars[0][self.pos(o)], bars[1][self.pos(o)]]
+        for ni in self.segs:
+            for k in range(ni):
+                fb = self.full[b]
+                yield lambda fb=fb, fph=fph: fb.passed(fph)
+                news = [O0 + k + 2] + ([O0, O0 + 1] if k == 0 else [])
+                for o in news:
+                    be, par = self.blk_empty[self.pos(o)], self.use(o) ^ 1
+                    yield lambda be=be, par=par: be.passed(par)
+                last = k == ni - 1
+                if (I & 1) == mw:
+                    tk, par = self.tok[mw], tph ^ (1 if mw == 0 else 0)
+                    yield lambda tk=tk, par=par: tk.passed(par)
+                    for o in news:
+                        for c in (0, 1):
+                            if self.blk_owner2[c][self.pos(o)] is not None:
+                                self.errors.append(f"CTA {c}: MMA into block {self.pos(o)} still owned by output {self.blk_owner2[c][self.pos(o)]}")
+                            self.blk_owner2[c][self.pos(o)] = o
+                    for c in (0, 1):
+                        if self.buf_row2[c][b] != I or self.tile_row2[c][b] != I:
+                            self.errors.append(f"row {I} issued from buffer {b} of CTA {c} holding row {self.buf_row2[c][b]} / landed {self.tile_row2[c][b]}")
+                    self.issued_by.setdefault(I, set()).add(mw)
+                    q = self.queues[mw]
+                    q.append(("mma", I))
+                    self.tok[mw ^ 1].arrive()
+                    outs = [O0 + k, O0 + k + 1] + ([O0] if k == 0 else []) + ([O0 + k + 1, O0 + k + 2, O0 + k + 2] if last else [])
+                    for o in outs:
+                        q.append(("commit", both(self.blk_full2, o)))
+                    tph ^= 1
+                else:
+                    for bar in both(self.blk_full2, O0 + k):
+                        bar.arrive()
+                    if last:
+                        self.queues[mw].append(("commit", both(self.blk_full2, O0 + k + 1)))
+                        for bar in both(self.blk_full2, O0 + k + 2):
+                            bar.arrive()
+                yield None
+                I += 1
+                b += 1
+                if b == self.D:
+                    b, fph = 0, fph ^ 1
+            O0 += ni + 2
+
+    def epilogue2(self, cta, wg):
+        O0, turn, row0 = 0, 0, 0
+        for ni in self.segs:
+            for j in range(ni + 2):
+                mine = turn == wg
+                turn = (turn + 1) % 3
+                if not mine:
+                    continue
+                o = O0 + j
+                bf, par = self.blk_full2[cta][self.pos(o)], self.use(o)
+                yield lambda bf=bf, par=par: bf.passed(par)
+                for k in (j - 2, j - 1, j):
+                    if 0 <= k < ni:
+                        g = row0 + k
+                        ts = self.issued_by.get(g, set())
+                        if ts != {g & 1} or any((t, g) not in self.mma_done for t in ts):
+                            self.errors.append(f"CTA {cta}: epilogue reads output {o} before row {g} completed (issued by {ts})")
+                if self.blk_owner2[cta][self.pos(o)] != o:
+                    self.errors.append(f"CTA {cta}: epilogue of output {o} finds block owned by {self.blk_owner2[cta][self.pos(o)]}")
+                self.blk_owner2[cta][self.pos(o)] = None
+                yield None
+                self.blk_empty[self.pos(o)].arrive()                 # (the peer's arrival is a remote one on the leader's barrier)
+            O0 += ni + 2
+            row0 += ni
+
+    def hw_step(self):
+        choices = (["tma"] if self.tma else []) + [t for t in (0, 1) if self.queues[t]]
+        if not choices:
+            return False
+        c = self.rng.choice(choices)
+        if c == "tma":
+            cta, b, row = self.tma.pop(self.rng.randrange(len(self.tma)))
+            self.tile_row2[cta][b] = row
+            self.full[b].arrive()                                    # complete_tx on the LEADER's barrier
+        else:
+            op = self.queues[c].pop(0)
+            if op[0] == "mma":
+                self.mma_done.add((c, op[1]))
+            else:
+                for bar in op[1]:                                    # multicast: not atomic across the two CTAs, but no agent
+                    bar.arrive()                                     # can tell (each CTA only reads its own copy)
+        return True
+
+
+def run_pair(nblk, stages, segments, seed):
+    rng = random.Random(seed)
+    m = PairModel(nblk, stages, segments, rng)
+    agents = {"prod0": m.producer2(0), "prod1": m.producer2(1), "mma0": m.issuer(0), "mma1": m.issuer(1)}
+    for c in (0, 1):
+        for wg in range(3):
+            agents[f"epi{c}{wg}"] = m.epilogue2(c, wg)
+    waiting = {k: None for k in agents}
+    frozen, frozen_for, steps = None, 0, 0
+    while agents:
+        steps += 1
+        assert steps < 4_000_000, "model did not terminate"
+        if frozen_for == 0 and rng.random() < 0.01:
+            frozen, frozen_for = rng.choice(list(agents)), rng.randrange(50, 400)
+        if frozen_for:
+            frozen_for -= 1
+        runnable = [k for k in agents if (waiting[k] is None or waiting[k]()) and not (frozen_for and k == frozen)]
+        if rng.random() < 0.5 or not runnable:
+            if m.hw_step():
+                continue
+            if not runnable:
+                if frozen_for:
+                    frozen_for = 0
+                    continue
+                return m, "deadlock: " + ", ".join(sorted(agents))
+        if not runnable:
+            continue
+        k = rng.choice(runnable)
+        try:
+            waiting[k] = next(agents[k])
+        except StopIteration:
+            del agents[k]
+            waiting.pop(k)
+    if m.tma or m.queues[0] or m.queues[1]:
+        m.errors.append(f"asynchronous work in flight when the CTAs leave: {len(m.tma)} loads, {len(m.queues[0]) + len(m.queues[1])} tensor-pipe ops")
+    return m, None
+
+
+@pytest.mark.parametrize("nblk,stages,segments", [(14, 2, [16]), (14, 5, [16]), (14, 3, [30]), (14, 5, [1, 14, 2]), (14, 2, [1] * 12),
+                                                  (14, 3, [3]), (14, 3, [1]), (14, 3, [4, 1]), (7, 5, [16]), (7, 2, [9, 7]), (7, 2, [1]),
+                                                  (7, 3, [2, 2, 2, 9]), (7, 2, [2] * 9), (14, 12, [40])])
+def test_pair_protocol_is_live_safe_and_quiescent_at_exit(nblk, stages, segments):
+    """The cta_group::2 variant (ring sizes of the shadow-block layout: 14, 7 with the conv1x1): live and safe in both
+    CTAs under arbitrary delays of any agent, and quiescent when the last agent finishes."""
+    for seed in range(120):
+        m, dead = run_pair(nblk, stages, segments, seed)
+        assert dead is None, (nblk, stages, segments, seed, dead)
+        assert not m.errors, (nblk, stages, segments, seed, m.errors[:3])
