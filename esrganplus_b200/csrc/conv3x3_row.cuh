@@ -228,7 +228,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     for (int i = 0; i < (p.chunk_bars ? D * p.num_chunks : D); ++i) mbar_init(&full_bar[i], 1);
     for (int i = 0; i < kMaxBlocks; ++i) {
       // row-alternating issue (row_alt == 2): + one plain arrival of the warp that does NOT issue the completing row
-      mbar_init(&blk_full[i], p.row_alt == 2 ? kRowMmaWarps + 1 : kRowMmaWarps);
+      mbar_init(&blk_full[i], (PAIR && p.pair_single) ? 1 : p.row_alt == 2 ? kRowMmaWarps + 1 : kRowMmaWarps);
       mbar_init(&blk_empty[i], PAIR ? 8 : 4);  // (PAIR: the four warps of a warpgroup of BOTH CTAs; only the leader's is used)
       mbar_arrive_cnt(&blk_empty[i], PAIR ? 8 : 4);  // phase 0 = "the block is free": complete from the start (no wait relies on the
                                           // parity of a phase that never existed; compute-sanitizer synccheck flags those)
@@ -382,6 +382,61 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     const bool alt = p.row_alt != 0;
     const int nfull = p.last_half ? nch - 1 : nch;  // chunks issued over all of their K-slices
     uint32_t a_lo = a_lo0;
+    if (PAIR && p.pair_single) {
+      // Experiment (ESRP_PAIR_SINGLE=1): ONE issuer thread for every row and ONE multicast commit per row (a commit tracks
+      // all earlier MMAs of its thread, so the commit of a row's "final" block covers the rows before it): block barriers
+      // count 1, the second issuer warp does nothing.  With cta_group::2 the issue is asynchronous (the pipe queues whole
+      // rows), so a single thread does not leave the bubbles it leaves on single CTAs.
+      if (mw == 0) {
+        SegWalk sw1(p, cta, ncta);
+        while (sw1.next(p)) {
+          const int ni = min(sw1.yb, p.h - 1) - max(sw1.ya - 1, 0) + 1;
+          for (int k = 0; k < ni; ++k) {
+            mbar_wait(&full_bar[b], fph);
+            const uint32_t On = O0 + k + 2;
+            if (k == 0) {
+              mbar_wait(&blk_empty[pos(O0)], use(O0));
+              mbar_wait(&blk_empty[pos(O0 + 1)], use(O0 + 1));
+            }
+            mbar_wait(&blk_empty[pos(On)], use(On));
+            tcgen05_fence_after();
+            const uint32_t dA = tmem_base + pos(On) * BN;
+            const uint32_t d_aux = tmem_base + AUX_COL0 + pos(O0 + k + 1) * BN;
+            if (elect_one()) {
+              uint32_t al = a_lo, bl = w_lo0;
+              for (int c = 0; c < nfull; ++c, al += chunk_step, bl += w_step) {
+                issue_taps<KC, BN, 0, false, KS, PAIR>(dA, dA, 0u, 0u, 0u, al, bl, DESC_HI, w_block_desc);
+                issue_taps<KC, BN, 1, false, KS, PAIR>(dA, dA, 0u, 0u, 0u, al, bl, DESC_HI, w_block_desc);
+              }
+              if (nfull < nch) {
+                issue_taps<KC, BN, 0, false, KS / 2, PAIR>(dA, dA, 0u, 0u, 0u, al, bl, DESC_HI, w_block_desc);
+                issue_taps<KC, BN, 1, false, KS / 2, PAIR>(dA, dA, 0u, 0u, 0u, al, bl, DESC_HI, w_block_desc);
+              }
+              if (AUX) {
+                al = a_lo;
+                bl = w_lo0;
+                for (int c = 0; c < naux; ++c, al += chunk_step, bl += w_step) {
+#pragma unroll
+                  for (int ks = 0; ks < KS; ++ks)
+                    umma_f16_ss2_2sm(d_aux, al + ((1 * RB + ks * 32) >> 4), DESC_HI,
+                                     bl + w_block_desc + ((aux_row0 * RB + ks * 32) >> 4), DESC_HI, idesc_aux,
+                                     (c | ks) != 0 ? 1u : 0u);
+                }
+              }
+              commit(&blk_full[pos(O0 + k)]);
+              if (k == ni - 1) {
+                commit(&blk_full[pos(O0 + k + 1)]);
+                commit(&blk_full[pos(O0 + k + 2)]);
+              }
+            }
+            __syncwarp();
+            a_lo += row_step;
+            if (++b == D) { b = 0; fph ^= 1; a_lo = a_lo0; }
+          }
+          O0 += static_cast<uint32_t>(ni + 2);
+        }
+      }
+    } else {
     SegWalk sw(p, cta, ncta);
     while (sw.next(p)) {
       const int ni = min(sw.yb, p.h - 1) - max(sw.ya - 1, 0) + 1;
@@ -537,6 +592,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
         if (++b == D) { b = 0; fph ^= 1; a_lo = a_lo0; }
       }
       O0 += static_cast<uint32_t>(ni + 2);
+    }
     }
     if (mw == 0 && lane == 0) trace_ev(p, 1, tn);
   } else {

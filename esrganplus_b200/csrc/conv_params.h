@@ -65,6 +65,7 @@ struct ConvKParams {
   int out_lo, ob_lo_c0;    // tile kernel: also store bf16(v - bf16(v)) at channel ob_lo_c0 of out_bf16 (esrp_conv3x3_t::out_lo)
   int chunk_bars;          // row kernel (row_alt, even ring depth, stages * num_chunks <= 8): one "data landed" barrier per K-chunk
                            // tile instead of one per row, so the MMAs of chunk c start when chunk c is there
+  int pair_single;         // row kernel, CTA pairs: one issuer thread, one multicast commit per row (experiment, ESRP_PAIR_SINGLE=1)
   int dbg;           // timing experiments only (ESRP_DBG_*): results are wrong when non-zero
   long long* trace;  // optional [3][1024] clock64 timeline of CTA 0 (see trace_ev)
 };

@@ -60,12 +60,14 @@ static int plan_row_t(const esrp_conv3x3_t& d, ConvLaunch* out) {
   p.no_quad = no_quad ? 1 : 0;
   static const int row_alt_env = [] { const char* e = getenv("ESRP_ROW_ALT"); return e ? atoi(e) : -1; }();
   const bool row_alt = row_alt_env >= 0 ? row_alt_env != 0 : (d.variant & ESRP_VARIANT_ROW_ALT) != 0;
+  static const bool pair_single = [] { const char* e = getenv("ESRP_PAIR_SINGLE"); return e && atoi(e) != 0; }();
+  p.pair_single = (PAIR && pair_single) ? 1 : 0;
   p.row_alt = row_alt ? 2 : 0;  // 2: alternate rows, the idle issuer adds the third arrival on the block barrier
   // One landed-barrier per K-chunk tile (full_bar[b * chunks + c]) where the eight barriers suffice (and, conservatively, the
   // ring depth is even: each issuer warp then meets every phase of the chunk barriers of "its" buffers): the MMAs of a row
   // start when its first chunk is there.  +1.2 .. 2.2 % on the benchmark forward (ESRP_CHUNK_BARS=0 switches it off).
   static const bool no_chunk_bars = [] { const char* e = getenv("ESRP_CHUNK_BARS"); return e && atoi(e) == 0; }();
-  p.chunk_bars = (!no_chunk_bars && row_alt && d.num_chunks >= 2 && nbuf * d.num_chunks <= kMaxStages && (nbuf % 2) == 0 &&
+  p.chunk_bars = (!no_chunk_bars && !p.pair_single && row_alt && d.num_chunks >= 2 && nbuf * d.num_chunks <= kMaxStages && (nbuf % 2) == 0 &&
                   (d.variant & 0x1F00) == 0) ? 1 : 0;   // (not under the ESRP_DBG_* timing variants)
   static const bool no_half = getenv("ESRP_NO_HALF_CHUNK") != nullptr;
   // K-slices of the last chunk beyond k_valid hold zero weights: do not issue them
