@@ -771,7 +771,8 @@ torch.save({"y": y.cpu(), "pairs": net._engines[x.device].num_pair_launches}, sy
 """
 
 
-def test_engine_with_cta_pairs_matches_default_engine(cuda_dev, tmp_path):
+@pytest.mark.parametrize("single", ["0", "1"])   # ESRP_PAIR_SINGLE: alternating issuers / one issuer thread, one commit per row
+def test_engine_with_cta_pairs_matches_default_engine(cuda_dev, tmp_path, single):
     """Whole generator (nb = 2, a batch of four 40 x 136 tiles: two column blocks, ragged width) with ESRP_PAIR=1 against the
     default engine, each in its own process: the dense-block convs run as cta_group::2 pairs over images (i, i + 2); the
     result agrees with the default path to the network tolerance of section 4.3 (same products, other summation order)."""
@@ -781,7 +782,7 @@ def test_engine_with_cta_pairs_matches_default_engine(cuda_dev, tmp_path):
     outs = []
     for pair in ("0", "1"):
         f = tmp_path / f"y{pair}.pt"
-        env = dict(os.environ, ESRP_PAIR=pair)
+        env = dict(os.environ, ESRP_PAIR=pair, ESRP_PAIR_SINGLE=single)
         r = subprocess.run([sys.executable, "-c", _PAIR_SCRIPT, root, str(f)], env=env, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(torch.load(f))
