@@ -323,10 +323,14 @@ class PairModel(Model):
     checks that NOTHING asynchronous is in flight when the last agent finishes — the moment both CTAs pass the final cluster
     barrier and leave (a multicast arrival after that would hit a CTA that is gone)."""
 
-    def __init__(self, nblk, stages, segments, rng):
+    def __init__(self, nblk, stages, segments, rng, single=False):
+        """single: ESRP_PAIR_SINGLE — one issuer thread issues every row and commits once per row; block barriers count 1."""
         super().__init__(2, nblk, stages, segments, rng, 1)
+        self.single = single
         self.full = [Bar(3) for _ in range(stages)]                 # leader producer + tile of CTA 0 + tile of CTA 1
-        self.blk_full2 = [self.blk_full, [Bar(3) for _ in range(nblk)]]
+        if single:
+            self.blk_full = [Bar(1) for _ in range(nblk)]
+        self.blk_full2 = [self.blk_full, [Bar(1 if single else 3) for _ in range(nblk)]]
         self.blk_empty = [Bar(2) for _ in range(nblk)]
         self.buf_row2 = [[None] * stages, [None] * stages]
         self.tile_row2 = [[None] * stages, [None] * stages]
@@ -366,7 +370,21 @@ class PairModel(Model):
                     be, par = self.blk_empty[self.pos(o)], self.use(o) ^ 1
                     yield lambda be=be, par=par: be.passed(par)
                 last = k == ni - 1
-                if (I & 1) == mw:
+                if self.single:
+                    for o in news:
+                        for c in (0, 1):
+                            if self.blk_owner2[c][self.pos(o)] is not None:
+                                self.errors.append(f"CTA {c}: MMA into block {self.pos(o)} still owned by output {self.blk_owner2[c][self.pos(o)]}")
+                            self.blk_owner2[c][self.pos(o)] = o
+                    for c in (0, 1):
+                        if self.buf_row2[c][b] != I or self.tile_row2[c][b] != I:
+                            self.errors.append(f"row {I} issued from buffer {b} of CTA {c} holding row {self.buf_row2[c][b]} / landed {self.tile_row2[c][b]}")
+                    self.issued_by.setdefault(I, set()).add(0)
+                    q = self.queues[0]
+                    q.append(("mma", I))
+                    for o in [O0 + k] + ([O0 + k + 1, O0 + k + 2] if last else []):
+                        q.append(("commit", both(self.blk_full2, o)))
+                elif (I & 1) == mw:
                     tk, par = self.tok[mw], tph ^ (1 if mw == 0 else 0)
                     yield lambda tk=tk, par=par: tk.passed(par)
                     for o in news:
@@ -414,7 +432,7 @@ class PairModel(Model):
                     if 0 <= k < ni:
                         g = row0 + k
                         ts = self.issued_by.get(g, set())
-                        if ts != {g & 1} or any((t, g) not in self.mma_done for t in ts):
+                        if ts != ({0} if self.single else {g & 1}) or any((t, g) not in self.mma_done for t in ts):
                             self.errors.append(f"CTA {cta}: epilogue reads output {o} before row {g} completed (issued by {ts})")
                 if self.blk_owner2[cta][self.pos(o)] != o:
                     self.errors.append(f"CTA {cta}: epilogue of output {o} finds block owned by {self.blk_owner2[cta][self.pos(o)]}")
@@ -443,10 +461,12 @@ class PairModel(Model):
         return True
 
 
-def run_pair(nblk, stages, segments, seed):
+def run_pair(nblk, stages, segments, seed, single=False):
     rng = random.Random(seed)
-    m = PairModel(nblk, stages, segments, rng)
-    agents = {"prod0": m.producer2(0), "prod1": m.producer2(1), "mma0": m.issuer(0), "mma1": m.issuer(1)}
+    m = PairModel(nblk, stages, segments, rng, single)
+    agents = {"prod0": m.producer2(0), "prod1": m.producer2(1), "mma0": m.issuer(0)}
+    if not single:
+        agents["mma1"] = m.issuer(1)
     for c in (0, 1):
         for wg in range(3):
             agents[f"epi{c}{wg}"] = m.epilogue2(c, wg)
@@ -484,10 +504,12 @@ def run_pair(nblk, stages, segments, seed):
 @pytest.mark.parametrize("nblk,stages,segments", [(14, 2, [16]), (14, 5, [16]), (14, 3, [30]), (14, 5, [1, 14, 2]), (14, 2, [1] * 12),
                                                   (14, 3, [3]), (14, 3, [1]), (14, 3, [4, 1]), (7, 5, [16]), (7, 2, [9, 7]), (7, 2, [1]),
                                                   (7, 3, [2, 2, 2, 9]), (7, 2, [2] * 9), (14, 12, [40])])
-def test_pair_protocol_is_live_safe_and_quiescent_at_exit(nblk, stages, segments):
-    """The cta_group::2 variant (ring sizes of the shadow-block layout: 14, 7 with the conv1x1): live and safe in both
-    CTAs under arbitrary delays of any agent, and quiescent when the last agent finishes."""
+@pytest.mark.parametrize("single", [False, True])
+def test_pair_protocol_is_live_safe_and_quiescent_at_exit(nblk, stages, segments, single):
+    """The cta_group::2 variant (ring sizes of the shadow-block layout: 14, 7 with the conv1x1), with the row-alternating
+    issuers and with ESRP_PAIR_SINGLE's one issuer thread / one commit per row: live and safe in both CTAs under arbitrary
+    delays of any agent, and quiescent when the last agent finishes."""
     for seed in range(120):
-        m, dead = run_pair(nblk, stages, segments, seed)
-        assert dead is None, (nblk, stages, segments, seed, dead)
-        assert not m.errors, (nblk, stages, segments, seed, m.errors[:3])
+        m, dead = run_pair(nblk, stages, segments, seed, single)
+        assert dead is None, (nblk, stages, segments, single, seed, dead)
+        assert not m.errors, (nblk, stages, segments, single, seed, m.errors[:3])
